@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py -- warped frames/s, forward+backward, of the fused flow-warp + occlusion-blend op.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One step = one forward + one backward (grad-input, grad-flow, grad-mask) of the op over one batch
+of synthetic Cityscapes-shaped frames (BASELINE.json configs[1]: 8 clips x 5 frames = 40 frames,
+C=64, 256x512, fp32, NCHW).  A frame is one [C,H,W] slice of the folded batch x frame axis.
+
+Prints ONE JSON line (rank 0).  Keys follow the driver's contract; see DESIGN.md "Measurement".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (frames per GPU, C, H, W, oob flow)
+    "cityscapes_256x512_c64": (40, 64, 256, 512, False),   # BASELINE.json configs[1] headline level
+    "kitti_256x832_c64_oob": (40, 64, 256, 832, True),     # configs[2]
+    "fullres_1024x2048_c256": (8, 256, 1024, 2048, False),  # configs[4]
+    "cpu_128x256_c64": (5, 64, 128, 256, False),           # configs[0]
+}
+METRIC = "warped frames/sec fwd+bwd @256x512 (fused flow-warp + occlusion blend, fp32)"
+
+
+def synth(N, C, H, W, oob, seed, device, pin=False):
+    """Synthetic inputs of SURVEY.md section 8d: x ~ N(0,1); flow = 8 px low-frequency field +
+    N(0,1) px noise (or the large / out-of-bounds variant); mask = sigmoid(N(0,1)); gout ~ N(0,1)."""
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(N, C, H, W, generator=g)
+    ii = torch.arange(H, dtype=torch.float32).view(1, H, 1)
+    jj = torch.arange(W, dtype=torch.float32).view(1, 1, W)
+    two_pi = 6.283185307179586
+    fx = 8.0 * torch.sin(two_pi * ii / (H / 2.0)) * torch.cos(two_pi * jj / (W / 2.0))
+    fy = 8.0 * torch.cos(two_pi * ii / (H / 2.0)) * torch.sin(two_pi * jj / (W / 2.0))
+    flow = torch.stack([fx.expand(N, H, W), fy.expand(N, H, W)], 1) + torch.randn(N, 2, H, W, generator=g)
+    if oob:
+        flow = torch.randn(N, 2, H, W, generator=g) * (W / 4.0)
+        sel = torch.rand(N, 1, H, W, generator=g) < 0.05
+        flow = torch.where(sel, torch.sign(flow) * 10.0 * W, flow)
+    mask = torch.sigmoid(torch.randn(N, 1, H, W, generator=g))
+    gout = torch.randn(N, C, H, W, generator=g)
+    ts = [x, flow.contiguous(), mask, gout]
+    if pin:
+        return [t.pin_memory() for t in ts]
+    return [t.to(device) for t in ts]
+
+
+def fwd_bytes(N, C, H, W):
+    return 4 * N * H * W * (2 * C + 3)
+
+
+def bwd_bytes(N, C, H, W):
+    return 4 * N * H * W * (3 * C + 6)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.t.join(2)
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for k, nme in enumerate(names):
+                if len(r) > 3 + k and r[3 + k].lower().startswith("active"):
+                    reasons.add(nme)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        busy = [v for v in sm if v > 0.5 * max(sm)] or sm
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def cpu_reference_run(workload, frames, steps, warmup, threads=None):
+    """The reference's CPU path (oracle.reference_torch: ops.py:187-202 + generator.py:93 restated
+    with the single device fix) fwd+bwd on `frames` frames of the workload, all host threads."""
+    from oracle import reference_torch as rt
+    _, C, H, W, oob = WORKLOADS[workload]
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    x, flow, mask, gout = synth(frames, C, H, W, oob, 1234, "cpu")
+    x.requires_grad_(True)
+    flow.requires_grad_(True)
+    mask.requires_grad_(True)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        out = rt.warp_blend(x, flow, mask)
+        torch.autograd.grad(out, [x, flow, mask], gout)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    return times, threads
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    workload = args.workload
+    frames = args.cpu_frames
+    times, threads = cpu_reference_run(workload, frames, args.steps, max(args.warmup, 1))
+    total = sum(times)
+    value = frames * len(times) / total
+    _, C, H, W, _ = WORKLOADS[workload]
+    sample = f"{frames} frames (C={C}, {H}x{W}) fwd+bwd per step, {len(times)} steps, torch {torch.__version__} CPU"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload, "frames_per_step": frames, "layout": "nchw",
+                   "note": "reference CPU path (oracle.reference_torch), bounded sample of the same workload"},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def run_ours(args):
+    import c2m_b200
+    from c2m_b200 import _lib
+    from c2m_b200 import dist as cdist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    rank, local_rank, world = cdist.init()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    _lib.load()
+    workload = args.workload
+    N, C, H, W, oob = WORKLOADS[workload]
+    if args.frames:
+        N = args.frames
+    nhwc = args.layout == "nhwc"
+    x, flow, mask, gout = synth(N, C, H, W, oob, 1234 + rank, dev)
+    if nhwc:
+        x = x.contiguous(memory_format=torch.channels_last)
+        gout = gout.contiguous(memory_format=torch.channels_last)
+    x.requires_grad_(True)
+    flow.requires_grad_(True)
+    mask.requires_grad_(True)
+    det = bool(args.deterministic)
+    flags = int(args.flags, 0)
+
+    def step(ev=None):
+        if ev:
+            ev[0].record()
+        out = c2m_b200.warp_blend(x, flow, mask, deterministic=det, flags=flags)
+        if ev:
+            ev[1].record()
+        g = torch.autograd.grad(out, [x, flow, mask], gout)
+        if ev:
+            ev[2].record()
+        return out, g
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = _lib.launch_count()
+    with ClockSampler(local_rank) as clk:
+        barrier()
+        t_begin.record()
+        for k in range(args.steps):
+            step(evs[k])
+        t_end.record()
+        barrier()
+    launches = _lib.launch_count() - launches0
+    ms_total = t_begin.elapsed_time(t_end)
+    fwd_ms = statistics.mean(e[0].elapsed_time(e[1]) for e in evs)
+    bwd_ms = statistics.mean(e[1].elapsed_time(e[2]) for e in evs)
+    value, ms_max, total_frames = cdist.aggregate_throughput(N * args.steps, ms_total, dev)
+
+    # ---- end to end through the public API with HOST buffers (pinned), copies inside the timed region
+    hx, hflow, hmask, hgout = synth(N, C, H, W, oob, 1234 + rank, dev, pin=True)
+    from c2m_b200 import host as chost
+    plan = chost.HostWarpPlan(N, C, H, W, dev, chunks=args.e2e_chunks, nhwc=False)
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    for _ in range(2):
+        plan.run(hx, hflow, hmask, hgout)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(e2e_steps):
+        plan.run(hx, hflow, hmask, hgout)
+    e1.record()
+    barrier()
+    e2e_value, _, _ = cdist.aggregate_throughput(N * e2e_steps, e0.elapsed_time(e1), dev)
+
+    peak, peak_src = measured_peak()
+    dominant = "bwd" if bwd_ms >= fwd_ms else "fwd"
+    dom_bytes = bwd_bytes(N, C, H, W) if dominant == "bwd" else fwd_bytes(N, C, H, W)
+    dom_ms = bwd_ms if dominant == "bwd" else fwd_ms
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+    roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": None, "kernel": f"{dominant} (c2m_warp_blend_{dominant}: all launches of the call)",
+            "peak_source": peak_src, "ms_per_launch": dom_ms,
+            "fwd": {"ms": fwd_ms, "achieved": fwd_bytes(N, C, H, W) / (fwd_ms * 1e-3) / 1e9},
+            "bwd": {"ms": bwd_ms, "achieved": bwd_bytes(N, C, H, W) / (bwd_ms * 1e-3) / 1e9},
+            "fwd_bwd": {"ms": fwd_ms + bwd_ms,
+                        "achieved": (fwd_bytes(N, C, H, W) + bwd_bytes(N, C, H, W)) / ((fwd_ms + bwd_ms) * 1e-3) / 1e9}}
+    roof["fwd_bwd"]["frac"] = roof["fwd_bwd"]["achieved"] / peak
+    tr = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tr):
+        try:
+            roof["traffic"] = json.load(open(tr)).get(f"{workload}:{args.layout}:{dominant}")
+        except Exception:
+            pass
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        times, threads = cpu_reference_run(workload, args.cpu_frames, 5, 2)
+        med = statistics.median(times)
+        cpu = {"value": args.cpu_frames / med, "unit": "frames/s", "cores": threads, "kind": "port",
+               "sample": f"{args.cpu_frames} frames (C={C}, {H}x{W}) fwd+bwd, median of 5 after 2 warm-ups, "
+                         f"oracle.reference_torch on torch {torch.__version__} CPU"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload, "frames_per_gpu": N, "C": C, "H": H, "W": W, "layout": args.layout,
+                       "grads": "input+flow+mask", "deterministic": det,
+                       "l2": "inputs (%.0f MB per tensor) larger than L2, no flush needed" % (4e-6 * N * C * H * W),
+                       "partition": "batch x frame, %d frames per rank, no collective" % N},
+            "roofline": roof, "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": plan.h2d_bytes,
+                    "d2h_bytes_per_step": plan.d2h_bytes, "steps": e2e_steps, "chunks": plan.chunks},
+            "gpu_launches": launches, "clocks": clk.summary(),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cityscapes_256x512_c64", choices=sorted(WORKLOADS))
+    ap.add_argument("--layout", default="nchw", choices=["nchw", "nhwc"])
+    ap.add_argument("--frames", type=int, default=0, help="override frames per GPU")
+    ap.add_argument("--deterministic", action="store_true")
+    ap.add_argument("--flags", default="0")
+    ap.add_argument("--cpu-frames", type=int, default=8, help="frames in the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-chunks", type=int, default=8)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,123 @@
+"""ctypes binding of libc2m_warp.so (the C ABI declared in include/c2m_warp.h).
+
+There is deliberately no fallback: if the shared library is missing or a call fails, the caller
+gets an exception -- never a silent PyTorch/CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libc2m_warp.so")
+
+PAD_BORDER = 0
+PAD_ZEROS = 1
+
+FLAG_DETERMINISTIC = 0x1
+FLAG_COORD_GRID = 0x2
+FLAG_TRUE_DIV = 0x100
+FLAG_NO_FMA = 0x200
+FLAG_FORCE_GENERIC = 0x400
+FLAG_NO_TMA = 0x800
+FLAG_BWD_ATOMIC = 0x1000
+
+# every symbol include/c2m_warp.h declares (tests/test_abi.py checks the list against the header)
+SYMBOLS = (
+    "c2m_warp_version",
+    "c2m_warp_last_error",
+    "c2m_warp_blend_fwd",
+    "c2m_warp_blend_bwd",
+    "c2m_warp_bwd_workspace_bytes",
+    "c2m_base_grid",
+    "c2m_warp_launch_count",
+)
+
+_lock = threading.Lock()
+_lib = None
+
+_i64 = ctypes.c_int64
+_int = ctypes.c_int
+_ptr = ctypes.c_void_p
+_Strides = _i64 * 4
+
+
+class C2MWarpError(RuntimeError):
+    pass
+
+
+def load(build_if_missing: bool = False) -> ctypes.CDLL:
+    """dlopen the library (once). Raises C2MWarpError if it is not there."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            if build_if_missing:
+                from . import _build
+                _build.build()
+            else:
+                raise C2MWarpError(
+                    f"{LIB_PATH} not found: build it with `python -m c2m_b200._build` "
+                    "(there is no fallback path)")
+        lib = ctypes.CDLL(LIB_PATH)
+        lib.c2m_warp_version.restype = _int
+        lib.c2m_warp_version.argtypes = []
+        lib.c2m_warp_last_error.restype = ctypes.c_char_p
+        lib.c2m_warp_last_error.argtypes = []
+        lib.c2m_warp_launch_count.restype = ctypes.c_uint64
+        lib.c2m_warp_launch_count.argtypes = []
+        lib.c2m_warp_blend_fwd.restype = _int
+        lib.c2m_warp_blend_fwd.argtypes = [_ptr, _ptr, _ptr, _ptr, _ptr, _i64, _int, _int, _int, _i64,
+                                           ctypes.POINTER(_i64), ctypes.POINTER(_i64), _int, _int, _ptr]
+        lib.c2m_warp_blend_bwd.restype = _int
+        lib.c2m_warp_blend_bwd.argtypes = [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr,
+                                           _i64, _int, _int, _int, _i64,
+                                           ctypes.POINTER(_i64), ctypes.POINTER(_i64), _int, _int,
+                                           _ptr, ctypes.c_size_t, _ptr]
+        lib.c2m_warp_bwd_workspace_bytes.restype = ctypes.c_size_t
+        lib.c2m_warp_bwd_workspace_bytes.argtypes = [_i64, _int, _int, _int, _i64, _int, _int]
+        lib.c2m_base_grid.restype = _int
+        lib.c2m_base_grid.argtypes = [_ptr, _i64, _int, _int, _ptr]
+        _lib = lib
+    return _lib
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().c2m_warp_last_error().decode("utf-8", "replace")
+        raise C2MWarpError(f"{what} failed (code {rc}): {msg}")
+
+
+def strides4(s) -> "_Strides":
+    return _Strides(*[int(v) for v in s])
+
+
+def warp_blend_fwd(x_ptr, flow_ptr, mask_ptr, other_ptr, out_ptr, N, C, H, W, x_batch, x_strides, out_strides,
+                   padding, flags, stream) -> None:
+    rc = load().c2m_warp_blend_fwd(x_ptr, flow_ptr, mask_ptr, other_ptr, out_ptr, N, C, H, W, x_batch,
+                                   strides4(x_strides), strides4(out_strides), padding, flags, stream)
+    _check(rc, "c2m_warp_blend_fwd")
+
+
+def warp_blend_bwd(x_ptr, flow_ptr, mask_ptr, other_ptr, gout_ptr, gx_ptr, gflow_ptr, gmask_ptr, gother_ptr,
+                   N, C, H, W, x_batch, x_strides, g_strides, padding, flags, ws_ptr, ws_bytes, stream) -> None:
+    rc = load().c2m_warp_blend_bwd(x_ptr, flow_ptr, mask_ptr, other_ptr, gout_ptr, gx_ptr, gflow_ptr, gmask_ptr,
+                                   gother_ptr, N, C, H, W, x_batch, strides4(x_strides), strides4(g_strides),
+                                   padding, flags, ws_ptr, ws_bytes, stream)
+    _check(rc, "c2m_warp_blend_bwd")
+
+
+def bwd_workspace_bytes(N, C, H, W, x_batch, want_gx, flags) -> int:
+    return int(load().c2m_warp_bwd_workspace_bytes(N, C, H, W, x_batch, int(bool(want_gx)), flags))
+
+
+def base_grid(grid_ptr, N, H, W, stream) -> None:
+    _check(load().c2m_base_grid(grid_ptr, N, H, W, stream), "c2m_base_grid")
+
+
+def launch_count() -> int:
+    return int(load().c2m_warp_launch_count())

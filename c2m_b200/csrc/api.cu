@@ -1,0 +1,242 @@
+// api.cu -- the C ABI of libc2m_warp.so (see include/c2m_warp.h) and host-side plumbing:
+// argument validation, layout classification, TMA descriptor encoding, error reporting.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace c2m {
+
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+int sm_count() {
+  static thread_local int cached_dev = -1, cached = 148;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev != cached_dev) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) cached = v;
+    cached_dev = dev;
+  }
+  return cached;
+}
+
+// cuTensorMapEncodeTiled is a driver-API symbol; it is resolved at run time so that the library
+// has no link-time dependency on libcuda (it must load on a machine without a GPU driver).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+    else
+      (void)cudaGetLastError();
+  });
+  return fn;
+}
+
+bool make_tensor_map_3d(CUtensorMap* tm, const float* base, int W, int H, int64_t planes, int box_w, int box_h,
+                        int box_p) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  if ((reinterpret_cast<uintptr_t>(base) & 15u) != 0 || (W & 3) != 0) return false;  // 16-byte base and pitches
+  if (box_w > 256 || box_h > 256 || box_p > 256) return false;
+  cuuint64_t gdim[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)planes};
+  cuuint64_t gstr[2] = {(cuuint64_t)W * sizeof(float), (cuuint64_t)W * H * sizeof(float)};
+  cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_p};
+  cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+static Layout classify(const int64_t s[4], int64_t N, int C, int H, int W) {
+  const int64_t HW = (int64_t)H * W;
+  auto ok = [](int64_t size, int64_t stride, int64_t want) { return size == 1 || stride == want; };
+  if (ok(C, s[1], HW) && ok(H, s[2], W) && ok(W, s[3], 1) && ok(N, s[0], (int64_t)C * HW)) return LAYOUT_NCHW;
+  if (ok(C, s[1], 1) && ok(H, s[2], (int64_t)W * C) && ok(W, s[3], C) && ok(N, s[0], (int64_t)C * HW)) return LAYOUT_NHWC;
+  return LAYOUT_OTHER;
+}
+
+static void canonical(int64_t dst[4], const int64_t src[4], Layout l, int C, int H, int W) {
+  // size-1 dimensions may carry arbitrary strides; rewrite them so kernels can trust the numbers
+  if (l == LAYOUT_NCHW) {
+    dst[0] = (int64_t)C * H * W; dst[1] = (int64_t)H * W; dst[2] = W; dst[3] = 1;
+  } else if (l == LAYOUT_NHWC) {
+    dst[0] = (int64_t)C * H * W; dst[1] = 1; dst[2] = (int64_t)W * C; dst[3] = C;
+  } else {
+    for (int k = 0; k < 4; ++k) dst[k] = src[k];
+  }
+}
+
+static int fill_dims(Dims& d, int64_t N, int C, int H, int W, int64_t x_batch, int padding, int flags) {
+  if (N < 0 || C < 0 || H < 0 || W < 0 || N > 0x7fffffff) {
+    set_error("invalid sizes N=%lld C=%d H=%d W=%d", (long long)N, C, H, W);
+    return C2M_ERR_INVALID;
+  }
+  if (padding != C2M_PAD_BORDER && padding != C2M_PAD_ZEROS) {
+    set_error("invalid padding %d", padding);
+    return C2M_ERR_INVALID;
+  }
+  if (x_batch <= 0) x_batch = N;
+  if (N > 0 && (x_batch > N || N % x_batch != 0)) {
+    set_error("x_batch=%lld must divide N=%lld", (long long)x_batch, (long long)N);
+    return C2M_ERR_INVALID;
+  }
+  d.N = (int)N; d.C = C; d.H = H; d.W = W;
+  d.x_batch = (int)(x_batch > 0 ? x_batch : 1);
+  d.padding = padding;
+  d.flags = flags;
+  // fp32 arithmetic exactly as torch.linspace / the reference's python scalars produce it
+  d.stepx = 2.0f / (float)(W - 1);
+  d.stepy = 2.0f / (float)(H - 1);
+  d.bw = (float)((W - 1.0) / 2.0);
+  d.bh = (float)((H - 1.0) / 2.0);
+  d.inv_bw = 1.0f / d.bw;
+  d.inv_bh = 1.0f / d.bh;
+  return C2M_OK;
+}
+
+static int check_launch(const char* what) {
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return C2M_ERR_CUDA;
+  }
+  return C2M_OK;
+}
+
+__global__ void base_grid_kernel(float* grid, int N, int H, int W, float stepx, float stepy) {
+  const int64_t HW = (int64_t)H * W;
+  const int64_t total = HW * N;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = idx / HW;
+    const int r = (int)(idx - n * HW);
+    const int i = r / W, j = r - i * W;
+    grid[n * 2 * HW + r] = base_coord(j, W, stepx);
+    grid[n * 2 * HW + HW + r] = base_coord(i, H, stepy);
+  }
+}
+
+}  // namespace c2m
+
+using namespace c2m;
+
+extern "C" {
+
+int c2m_warp_version(void) { return C2M_WARP_VERSION; }
+const char* c2m_warp_last_error(void) { return g_err; }
+uint64_t c2m_warp_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int c2m_warp_blend_fwd(const float* x, const float* flow, const float* mask, const float* other, float* out,
+                       int64_t N, int C, int H, int W, int64_t x_batch, const int64_t x_strides[4],
+                       const int64_t out_strides[4], int padding, int flags, void* cuda_stream) {
+  FwdParams p;
+  memset(&p, 0, sizeof(p));
+  int rc = fill_dims(p.d, N, C, H, W, x_batch, padding, flags);
+  if (rc) return rc;
+  if (N == 0 || C == 0 || H == 0 || W == 0) return C2M_OK;  // empty: nothing to write
+  if (!x || !flow || !out || !x_strides || !out_strides) {
+    set_error("null pointer argument");
+    return C2M_ERR_INVALID;
+  }
+  if (other && !mask) {
+    set_error("`other` requires a mask");
+    return C2M_ERR_INVALID;
+  }
+  const Layout lx = classify(x_strides, p.d.x_batch, C, H, W), lo = classify(out_strides, N, C, H, W);
+  canonical(p.xs, x_strides, lx, C, H, W);
+  canonical(p.os, out_strides, lo, C, H, W);
+  p.x = x; p.flow = flow; p.mask = mask; p.other = other; p.out = out;
+  p.cchunk = C;
+  rc = launch_fwd(p, lx, lo, reinterpret_cast<cudaStream_t>(cuda_stream));
+  if (rc) return rc;
+  return check_launch("c2m_warp_blend_fwd");
+}
+
+size_t c2m_warp_bwd_workspace_bytes(int64_t N, int C, int H, int W, int64_t x_batch, int want_gx, int flags) {
+  return bwd_workspace_bytes(N, C, H, W, x_batch, want_gx, flags);
+}
+
+int c2m_warp_blend_bwd(const float* x, const float* flow, const float* mask, const float* other, const float* gout,
+                       float* gx, float* gflow, float* gmask, float* gother, int64_t N, int C, int H, int W,
+                       int64_t x_batch, const int64_t x_strides[4], const int64_t g_strides[4], int padding,
+                       int flags, void* workspace, size_t workspace_bytes, void* cuda_stream) {
+  BwdParams p;
+  memset(&p, 0, sizeof(p));
+  int rc = fill_dims(p.d, N, C, H, W, x_batch, padding, flags);
+  if (rc) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
+  if (N == 0 || H == 0 || W == 0) return C2M_OK;
+  if (C == 0) {  // no channels: flow / mask gradients are zero
+    if (gflow && cudaMemsetAsync(gflow, 0, (size_t)N * 2 * H * W * sizeof(float), st) != cudaSuccess) return C2M_ERR_CUDA;
+    if (gmask && cudaMemsetAsync(gmask, 0, (size_t)N * H * W * sizeof(float), st) != cudaSuccess) return C2M_ERR_CUDA;
+    return C2M_OK;
+  }
+  if (!x || !flow || !gout || !x_strides || !g_strides) {
+    set_error("null pointer argument");
+    return C2M_ERR_INVALID;
+  }
+  if ((other || gother) && !mask) {
+    set_error("`other` requires a mask");
+    return C2M_ERR_INVALID;
+  }
+  if (gmask && !mask) {
+    set_error("gmask requested without a mask");
+    return C2M_ERR_INVALID;
+  }
+  const Layout lx = classify(x_strides, p.d.x_batch, C, H, W), lg = classify(g_strides, N, C, H, W);
+  if (gx && lx == LAYOUT_OTHER) {
+    set_error("grad-input needs x to be NCHW- or NHWC-dense");
+    return C2M_ERR_INVALID;
+  }
+  canonical(p.xs, x_strides, lx, C, H, W);
+  canonical(p.gs, g_strides, lg, C, H, W);
+  p.x = x; p.flow = flow; p.mask = mask; p.other = other; p.gout = gout;
+  p.gx = gx; p.gflow = gflow; p.gmask = gmask; p.gother = gother;
+  p.cchunk = C;
+  rc = launch_bwd(p, lx, lg, workspace, workspace_bytes, st);
+  if (rc) return rc;
+  return check_launch("c2m_warp_blend_bwd");
+}
+
+int c2m_base_grid(float* grid, int64_t N, int H, int W, void* cuda_stream) {
+  if (N < 0 || H < 0 || W < 0 || N > 0x7fffffff) {
+    set_error("invalid sizes");
+    return C2M_ERR_INVALID;
+  }
+  if (N == 0 || H == 0 || W == 0) return C2M_OK;
+  if (!grid) {
+    set_error("null pointer argument");
+    return C2M_ERR_INVALID;
+  }
+  const int64_t total = N * H * W;
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  base_grid_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(cuda_stream)>>>(
+      grid, (int)N, H, W, 2.0f / (float)(W - 1), 2.0f / (float)(H - 1));
+  count_launch();
+  return check_launch("c2m_base_grid");
+}
+
+}  // extern "C"

@@ -1,0 +1,208 @@
+// common.cuh -- shared device/host helpers for the C2M warp kernels (sm_100a only).
+//
+// Coordinate arithmetic is a bit-replica of what the reference computes on a GPU
+// (SURVEY.md appendix A.3):
+//   base grid     torch CPU float32 linspace(-1,1,n) (reference src/utils/ops.py:196-202)
+//   normalisation flow * (1.f / (float)((n-1)/2))     (ops.py:190; ATen CUDA div-by-scalar)
+//   grid add      one fp32 add                         (ops.py:191)
+//   unnormalise   fma(c + 1, n, -1) * 0.5              (ATen GridSampler.cuh:22-31, align_corners=False)
+//   border clip   min(n-1, max(c, 0))                  (GridSampler.cuh:55-58)
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/c2m_warp.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "c2m_b200 kernels target sm_100a only"
+#endif
+
+namespace c2m {
+
+struct Dims {
+  int N, C, H, W;
+  int x_batch;  // distinct images in x (== N when there is no repeat)
+  int padding, flags;
+  float stepx, stepy;    // fp32 2/(n-1), as torch.linspace computes it
+  float inv_bw, inv_bh;  // fp32 1/((n-1)/2)
+  float bw, bh;          // fp32 (n-1)/2 (only for the TRUE_DIV probe variant)
+};
+
+struct FwdParams {
+  Dims d;
+  const float* x;
+  const float* flow;
+  const float* mask;
+  const float* other;
+  float* out;
+  int64_t xs[4], os[4];
+  int cchunk;  // channels per blockIdx.y slice
+};
+
+struct BwdParams {
+  Dims d;
+  const float* x;
+  const float* flow;
+  const float* mask;
+  const float* other;
+  const float* gout;
+  float* gx;
+  float* gflow;
+  float* gmask;
+  float* gother;
+  int64_t xs[4], gs[4];
+  int cchunk;
+  // deterministic mode
+  long long* acc64;         // fixed-point accumulator, same element order as gx
+  const unsigned* maxbits;  // bit pattern of max|gout*mask|
+  int count_log2;           // ceil(log2(max contributions per destination))
+};
+
+// Per-pixel sampling geometry, shared by forward and backward.
+struct Geo {
+  float wnw, wne, wsw, wse;  // bilinear weights (ATen order nw, ne, sw, se)
+  int x0, y0, x1, y1;        // corner indices, clamped into the image (loads are always legal)
+  bool oknw, okne, oksw, okse;
+  float gmx, gmy;            // d(clipped coord)/d(flow) = size/2 * clip-grad * inv_b
+  float ax, ay;              // ix - x0, iy - y0 (for the coordinate gradient)
+};
+
+__device__ __forceinline__ float base_coord(int k, int n, float step) {
+  // torch CPU linspace: first half fma(step,k,-1), second half fma(-step,n-1-k,1); n==1 -> -1
+  if (n == 1) return -1.f;
+  return (k < (n >> 1)) ? fmaf(step, (float)k, -1.f) : fmaf(-step, (float)(n - 1 - k), 1.f);
+}
+
+__device__ __forceinline__ float unnormalized(float f, int k, int n, float step, float inv_b, float b,
+                                              int flags) {
+  const float g = base_coord(k, n, step);
+  // intrinsics keep nvcc from contracting across the reference's materialised temporaries
+  const float nf = (flags & C2M_FLAG_TRUE_DIV) ? __fdiv_rn(f, b) : __fmul_rn(f, inv_b);
+  const float c1 = __fadd_rn(__fadd_rn(g, nf), 1.f);
+  const float u = (flags & C2M_FLAG_NO_FMA) ? __fadd_rn(__fmul_rn(c1, (float)n), -1.f)
+                                            : fmaf(c1, (float)n, -1.f);
+  return u * 0.5f;
+}
+
+// BWD selects ATen's clip_coordinates_set_grad behaviour (NaN is not clipped there and ends up at
+// -100 through safe_downgrade_to_int_range, GridSampler.cuh:64-82,141-148).
+template <bool BWD>
+__device__ __forceinline__ void make_geo(const Dims& d, float fx, float fy, int i, int j, Geo& g) {
+  float ix, iy;
+  float sx = d.inv_bw, sy = d.inv_bh;
+  if (d.flags & C2M_FLAG_COORD_GRID) {
+    // (fx, fy) is a normalised sampling location (reference utils.grid_sample, ops.py:183-184)
+    ix = fmaf(__fadd_rn(fx, 1.f), (float)d.W, -1.f) * 0.5f;
+    iy = fmaf(__fadd_rn(fy, 1.f), (float)d.H, -1.f) * 0.5f;
+    sx = 1.f;
+    sy = 1.f;
+  } else {
+    ix = unnormalized(fx, j, d.W, d.stepx, d.inv_bw, d.bw, d.flags);
+    iy = unnormalized(fy, i, d.H, d.stepy, d.inv_bh, d.bh, d.flags);
+  }
+  float cgx = 1.f, cgy = 1.f;
+  if (d.padding == C2M_PAD_BORDER) {
+    if (BWD) {
+      cgx = (ix > 0.f && ix < (float)(d.W - 1)) ? 1.f : 0.f;
+      cgy = (iy > 0.f && iy < (float)(d.H - 1)) ? 1.f : 0.f;
+      ix = (ix != ix) ? -100.f : fminf((float)(d.W - 1), fmaxf(ix, 0.f));
+      iy = (iy != iy) ? -100.f : fminf((float)(d.H - 1), fmaxf(iy, 0.f));
+    } else {
+      ix = fminf((float)(d.W - 1), fmaxf(ix, 0.f));  // fmaxf(NaN,0)=0, as ATen's ::max
+      iy = fminf((float)(d.H - 1), fmaxf(iy, 0.f));
+    }
+  } else {
+    if (!(ix <= 2147483646.f && ix >= -2147483648.f)) ix = -100.f;  // also catches NaN / inf
+    if (!(iy <= 2147483646.f && iy >= -2147483648.f)) iy = -100.f;
+  }
+  const float fx0 = floorf(ix), fy0 = floorf(iy);
+  const float fx1 = fx0 + 1.f, fy1 = fy0 + 1.f;
+  g.wnw = (fx1 - ix) * (fy1 - iy);
+  g.wne = (ix - fx0) * (fy1 - iy);
+  g.wsw = (fx1 - ix) * (iy - fy0);
+  g.wse = (ix - fx0) * (iy - fy0);
+  g.ax = ix - fx0;
+  g.ay = iy - fy0;
+  const int x0 = (int)fx0, y0 = (int)fy0, x1 = x0 + 1, y1 = y0 + 1;
+  const bool x0ok = (x0 >= 0) & (x0 < d.W), x1ok = (x1 >= 0) & (x1 < d.W);
+  const bool y0ok = (y0 >= 0) & (y0 < d.H), y1ok = (y1 >= 0) & (y1 < d.H);
+  g.oknw = x0ok & y0ok;
+  g.okne = x1ok & y0ok;
+  g.oksw = x0ok & y1ok;
+  g.okse = x1ok & y1ok;
+  g.x0 = min(max(x0, 0), d.W - 1);
+  g.x1 = min(max(x1, 0), d.W - 1);
+  g.y0 = min(max(y0, 0), d.H - 1);
+  g.y1 = min(max(y1, 0), d.H - 1);
+  // ATen: grad_grid = (size/2 * clip_grad) * gix; autograd of ops.py:190 multiplies by 1/((size-1)/2)
+  g.gmx = cgx * (0.5f * (float)d.W) * sx;
+  g.gmy = cgy * (0.5f * (float)d.H) * sy;
+}
+
+// ---------------------------------------------------------------------------------------------
+// mbarrier + TMA (cp.async.bulk.tensor) wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "C2M_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra C2M_DONE;\n"
+      "bra C2M_WAIT;\n"
+      "C2M_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// 3-D tiled tensor load: coordinates are (innermost, middle, outermost) element indices.
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1,
+                                            int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::
+          "r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
+
+// streaming (evict-first) accesses for data touched exactly once
+__device__ __forceinline__ void st_stream(float* p, float v) { __stcs(p, v); }
+__device__ __forceinline__ void st_stream(float4* p, float4 v) { __stcs(p, v); }
+__device__ __forceinline__ float ld_stream(const float* p) { return __ldcs(p); }
+__device__ __forceinline__ float4 ld_stream(const float4* p) { return __ldcs(p); }
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+enum Layout { LAYOUT_NCHW = 0, LAYOUT_NHWC = 1, LAYOUT_OTHER = 2 };
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+int sm_count();
+// Encodes a [planes, H, W] float32 tensor map with box (box_w, box_h, box_p); returns false when
+// the tensor does not satisfy TMA's alignment rules (caller falls back to plain loads).
+bool make_tensor_map_3d(CUtensorMap* tm, const float* base, int W, int H, int64_t planes, int box_w, int box_h,
+                        int box_p);
+
+int launch_fwd(const FwdParams& p, Layout lx, Layout lo, cudaStream_t st);
+int launch_bwd(const BwdParams& p, Layout lx, Layout lg, void* workspace, size_t workspace_bytes, cudaStream_t st);
+size_t bwd_workspace_bytes(int64_t N, int C, int H, int W, int64_t x_batch, int want_gx, int flags);
+
+}  // namespace c2m

@@ -1,0 +1,183 @@
+// warp_bwd.cu -- fused backward of the flow-warp + occlusion blend: grad-input (scatter), grad-flow,
+// grad-mask (and grad-other).  Replaces the autograd graph of reference src/utils/ops.py:187-193 +
+// src/modules/generator/generator.py:93: mul backward (2 kernels + a C-reduction), ATen
+// grid_sampler_2d_backward (zero-fill + 4 atomics per element), add/cat/div backward.
+//
+// Nothing is saved by the forward except its inputs: coordinates and weights are recomputed here.
+//
+// Kernels in this file
+//   bwd_scatter_kernel    stride-generic, one thread per pixel, channel loop; grad-input by global
+//                         red.add (fp32) or, in deterministic mode, by order-independent 64-bit
+//                         fixed-point atomics into a workspace that fix2float_kernel converts.
+//   absmax_kernel         max |gout * mask| (sets the fixed-point scale; order independent).
+#include "common.cuh"
+
+namespace c2m {
+
+__device__ __forceinline__ void red_add(float* p, float v) { atomicAdd(p, v); }
+
+template <bool DET>
+__device__ __forceinline__ void scatter_add(const BwdParams& p, int64_t off, float v, float scale) {
+  if (DET) {
+    const long long q = __double2ll_rn((double)v * (double)scale);
+    atomicAdd(reinterpret_cast<unsigned long long*>(p.acc64 + off), (unsigned long long)q);
+  } else {
+    red_add(p.gx + off, v);
+  }
+}
+
+// scale = 2^(61 - count_log2 - exponent(max)), so that count * max * scale < 2^62
+__device__ __forceinline__ float fixed_scale(const BwdParams& p) {
+  const float mx = __uint_as_float(*p.maxbits);
+  int e = 0;
+  if (mx > 0.f && mx < 3.0e38f) frexpf(mx, &e);
+  int k = 61 - p.count_log2 - e;
+  k = max(-120, min(120, k));
+  return exp2f((float)k);
+}
+
+template <bool DET, bool HAS_OTHER>
+__global__ void __launch_bounds__(256) bwd_scatter_kernel(const BwdParams p) {
+  const Dims& d = p.d;
+  const int64_t HW = (int64_t)d.H * d.W;
+  const int64_t total = HW * d.N;
+  const bool need_x = (p.gflow != nullptr) || (p.gmask != nullptr);
+  const float scale = DET ? fixed_scale(p) : 1.f;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int n = (int)(idx / HW);
+    const int r = (int)(idx - (int64_t)n * HW);
+    const int i = r / d.W, j = r - i * d.W;
+    const bool gridmode = (d.flags & C2M_FLAG_COORD_GRID) != 0;
+    const float* fl = gridmode ? p.flow + ((int64_t)n * HW + r) * 2 : p.flow + (int64_t)n * 2 * HW + r;
+    const float fx = fl[0], fy = fl[gridmode ? 1 : HW];
+    const float m = p.mask ? p.mask[(int64_t)n * HW + r] : 1.f;
+    Geo g;
+    make_geo<true>(d, fx, fy, i, j, g);
+    const int64_t xbase = (int64_t)(n % d.x_batch) * p.xs[0];
+    const int64_t onw = g.y0 * p.xs[2] + g.x0 * p.xs[3], one = g.y0 * p.xs[2] + g.x1 * p.xs[3];
+    const int64_t osw = g.y1 * p.xs[2] + g.x0 * p.xs[3], ose = g.y1 * p.xs[2] + g.x1 * p.xs[3];
+    const int64_t gb = (int64_t)n * p.gs[0] + i * p.gs[2] + j * p.gs[3];
+    float gix = 0.f, giy = 0.f, gm = 0.f;
+    for (int c = 0; c < d.C; ++c) {
+      const float go = p.gout[gb + c * p.gs[1]];
+      const float gg = p.mask ? go * m : go;
+      const int64_t xc = xbase + c * p.xs[1];
+      if (p.gx) {
+        if (g.oknw) scatter_add<DET>(p, xc + onw, g.wnw * gg, scale);
+        if (g.okne) scatter_add<DET>(p, xc + one, g.wne * gg, scale);
+        if (g.oksw) scatter_add<DET>(p, xc + osw, g.wsw * gg, scale);
+        if (g.okse) scatter_add<DET>(p, xc + ose, g.wse * gg, scale);
+      }
+      if (need_x) {
+        const float vnw = g.oknw ? p.x[xc + onw] : 0.f, vne = g.okne ? p.x[xc + one] : 0.f;
+        const float vsw = g.oksw ? p.x[xc + osw] : 0.f, vse = g.okse ? p.x[xc + ose] : 0.f;
+        // d out / d ix, d out / d iy (ATen grid_sampler_2d_backward)
+        gix = fmaf(gg, (vne - vnw) * (1.f - g.ay) + (vse - vsw) * g.ay, gix);
+        giy = fmaf(gg, (vsw - vnw) * (1.f - g.ax) + (vse - vne) * g.ax, giy);
+        float warped = vnw * g.wnw;
+        warped = fmaf(vne, g.wne, warped);
+        warped = fmaf(vsw, g.wsw, warped);
+        warped = fmaf(vse, g.wse, warped);
+        if (HAS_OTHER) warped -= p.other[gb + c * p.gs[1]];
+        gm = fmaf(go, warped, gm);
+      }
+      if (HAS_OTHER && p.gother) p.gother[gb + c * p.gs[1]] = go * (1.f - m);
+    }
+    if (p.gflow) {
+      float* gf = gridmode ? p.gflow + ((int64_t)n * HW + r) * 2 : p.gflow + (int64_t)n * 2 * HW + r;
+      gf[0] = gix * g.gmx;
+      gf[gridmode ? 1 : HW] = giy * g.gmy;
+    }
+    if (p.gmask) p.gmask[(int64_t)n * HW + r] = gm;
+  }
+}
+
+__global__ void __launch_bounds__(256) absmax_kernel(const BwdParams p, unsigned* out_bits) {
+  const Dims& d = p.d;
+  const int64_t HW = (int64_t)d.H * d.W;
+  const int64_t total = HW * d.N;
+  float mx = 0.f;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int n = (int)(idx / HW);
+    const int r = (int)(idx - (int64_t)n * HW);
+    const int i = r / d.W, j = r - i * d.W;
+    const float m = p.mask ? fabsf(p.mask[(int64_t)n * HW + r]) : 1.f;
+    const int64_t gb = (int64_t)n * p.gs[0] + i * p.gs[2] + j * p.gs[3];
+    for (int c = 0; c < d.C; ++c) {
+      const float v = fabsf(p.gout[gb + c * p.gs[1]]) * m;
+      mx = (v == v) ? fmaxf(mx, v) : mx;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0 && mx > 0.f) atomicMax(out_bits, __float_as_uint(mx));  // non-negative: bits are ordered
+}
+
+__global__ void __launch_bounds__(256) fix2float_kernel(const long long* acc, float* gx, int64_t n, BwdParams p) {
+  const double inv = 1.0 / (double)fixed_scale(p);
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x)
+    gx[idx] = (float)((double)acc[idx] * inv);
+}
+
+// ---------------------------------------------------------------------------------------------
+size_t bwd_workspace_bytes(int64_t N, int C, int H, int W, int64_t x_batch, int want_gx, int flags) {
+  (void)N;
+  size_t b = 256;
+  if (want_gx && (flags & C2M_FLAG_DETERMINISTIC)) {
+    const int64_t xb = x_batch > 0 ? x_batch : N;
+    b += (size_t)xb * C * H * W * sizeof(long long);
+  }
+  return b;
+}
+
+static int grid_for(int64_t total) {
+  int64_t blocks = (total + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 32;
+  return (int)(blocks > cap ? cap : (blocks < 1 ? 1 : blocks));
+}
+
+int launch_bwd(const BwdParams& pin, Layout lx, Layout lg, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  (void)lx;
+  (void)lg;
+  BwdParams p = pin;
+  const Dims& d = p.d;
+  const int64_t total = (int64_t)d.N * d.H * d.W;
+  const int64_t nx = (int64_t)d.x_batch * d.C * d.H * d.W;
+  const bool det = (d.flags & C2M_FLAG_DETERMINISTIC) && p.gx;
+  const size_t need = bwd_workspace_bytes(d.N, d.C, d.H, d.W, d.x_batch, p.gx != nullptr, d.flags);
+  if (det && (workspace == nullptr || workspace_bytes < need)) {
+    set_error("workspace too small: %zu < %zu", workspace_bytes, need);
+    return C2M_ERR_WORKSPACE;
+  }
+  if (det) {
+    // gx must be dense in memory for the fixed-point accumulator to mirror it
+    unsigned* maxbits = reinterpret_cast<unsigned*>(workspace);
+    p.acc64 = reinterpret_cast<long long*>(reinterpret_cast<char*>(workspace) + 256);
+    p.maxbits = maxbits;
+    int cl = 2;  // 4 corners
+    int64_t cnt = (int64_t)d.H * d.W * (d.N / d.x_batch);
+    while ((1ll << (cl - 2)) < cnt) ++cl;
+    p.count_log2 = cl;
+    if (cudaMemsetAsync(workspace, 0, 256 + (size_t)nx * sizeof(long long), st) != cudaSuccess) return C2M_ERR_CUDA;
+    absmax_kernel<<<grid_for(total), 256, 0, st>>>(p, maxbits);
+    count_launch();
+  } else if (p.gx) {
+    if (cudaMemsetAsync(p.gx, 0, (size_t)nx * sizeof(float), st) != cudaSuccess) return C2M_ERR_CUDA;
+  }
+  const int grid = grid_for(total);
+  if (det) {
+    if (p.other) bwd_scatter_kernel<true, true><<<grid, 256, 0, st>>>(p);
+    else bwd_scatter_kernel<true, false><<<grid, 256, 0, st>>>(p);
+    count_launch();
+    fix2float_kernel<<<grid_for(nx), 256, 0, st>>>(p.acc64, p.gx, nx, p);
+    count_launch();
+  } else {
+    if (p.other) bwd_scatter_kernel<false, true><<<grid, 256, 0, st>>>(p);
+    else bwd_scatter_kernel<false, false><<<grid, 256, 0, st>>>(p);
+    count_launch();
+  }
+  return C2M_OK;
+}
+
+}  // namespace c2m

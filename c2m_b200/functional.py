@@ -1,0 +1,131 @@
+"""torch.autograd.Function over the C ABI: the fused flow-warp + occlusion-blend op.
+
+Contract in reference terms (PierfrancescoArdino/C2M):
+    warp_blend(x, flow, mask) == utils.resample(x, flow) * mask
+        src/utils/ops.py:187-193, src/modules/generator/generator.py:93
+on CUDA float32 tensors, forward and backward, in one kernel each way.  PyTorch is used for
+device memory, streams and autograd bookkeeping only; the arithmetic runs in libc2m_warp.so.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+from torch.autograd.function import once_differentiable
+
+from . import _lib
+
+_PADDING = {"border": _lib.PAD_BORDER, "zeros": _lib.PAD_ZEROS}
+
+
+def deterministic_default() -> bool:
+    """Deterministic grad-input is selected by torch's global switch or C2M_WARP_DETERMINISTIC=1
+    (no new YAML keys in the reference's config)."""
+    if os.environ.get("C2M_WARP_DETERMINISTIC", "0") not in ("", "0"):
+        return True
+    return torch.are_deterministic_algorithms_enabled()
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _is_nhwc_dense(t: torch.Tensor) -> bool:
+    return (t.dim() == 4 and not t.is_contiguous() and t.is_contiguous(memory_format=torch.channels_last))
+
+
+def _dense(t: torch.Tensor, nhwc: bool) -> torch.Tensor:
+    return t.contiguous(memory_format=torch.channels_last) if nhwc else t.contiguous()
+
+
+def _check_inputs(x, flow, mask, other):
+    for name, t in (("x", x), ("flow", flow), ("mask", mask), ("other", other)):
+        if t is None:
+            continue
+        if not t.is_cuda:
+            # the reference itself cannot run this path on CPU tensors (ops.py:189,202)
+            raise RuntimeError(f"c2m_b200.warp_blend: `{name}` must be a CUDA tensor (no CPU fallback)")
+        if t.dtype != torch.float32:
+            raise TypeError(f"c2m_b200.warp_blend: `{name}` must be float32, got {t.dtype}")
+        if t.device != x.device:
+            raise RuntimeError("c2m_b200.warp_blend: all tensors must be on the same device")
+    if x.dim() != 4 or flow.dim() != 4 or flow.shape[1] != 2:
+        raise ValueError(f"expected x [B,C,H,W] and flow [N,2,H,W], got {tuple(x.shape)} and {tuple(flow.shape)}")
+    N, _, H, W = flow.shape
+    if tuple(x.shape[2:]) != (H, W):
+        raise ValueError(f"flow {tuple(flow.shape)} does not match x {tuple(x.shape)} spatially")
+    B = x.shape[0]
+    if B != N and (B == 0 or N % B != 0):
+        raise ValueError(f"x batch {B} must equal or divide the flow batch {N}")
+    if mask is not None and tuple(mask.shape) != (N, 1, H, W):
+        raise ValueError(f"mask must be [N,1,H,W]={N, 1, H, W}, got {tuple(mask.shape)}")
+    if other is not None:
+        if mask is None:
+            raise ValueError("`other` requires a mask")
+        if tuple(other.shape) != (N, x.shape[1], H, W):
+            raise ValueError("`other` must have the output's shape")
+
+
+class WarpBlendFunction(torch.autograd.Function):
+    """out = mask * bilinear_border_warp(x, flow) [+ (1 - mask) * other]."""
+
+    @staticmethod
+    def forward(ctx, x, flow, mask, other, padding, deterministic, flags):
+        _check_inputs(x, flow, mask, other)
+        nhwc = _is_nhwc_dense(x)
+        x = _dense(x, nhwc)
+        flow = flow.contiguous()
+        mask = None if mask is None else mask.contiguous()
+        other = None if other is None else _dense(other, nhwc)
+        N, _, H, W = flow.shape
+        B, C = x.shape[0], x.shape[1]
+        out = torch.empty((N, C, H, W), dtype=x.dtype, device=x.device,
+                          memory_format=torch.channels_last if nhwc else torch.contiguous_format)
+        with torch.cuda.device(x.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            _lib.warp_blend_fwd(_ptr(x), _ptr(flow), _ptr(mask), _ptr(other), _ptr(out), N, C, H, W, B,
+                                x.stride(), out.stride(), padding, flags, stream)
+        ctx.save_for_backward(x, flow, mask, other)  # inputs only: geometry is recomputed in backward
+        ctx.cfg = (padding, bool(deterministic), flags, nhwc)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout):
+        x, flow, mask, other = ctx.saved_tensors
+        padding, deterministic, flags, nhwc = ctx.cfg
+        need_x, need_flow, need_mask, need_other = ctx.needs_input_grad[:4]
+        need_mask = need_mask and mask is not None
+        need_other = need_other and other is not None
+        gout = _dense(gout, nhwc)
+        N, _, H, W = flow.shape
+        B, C = x.shape[0], x.shape[1]
+        gx = torch.empty_like(x) if need_x else None
+        gflow = torch.empty_like(flow) if need_flow else None
+        gmask = torch.empty_like(mask) if need_mask else None
+        gother = torch.empty_like(gout) if need_other else None
+        if deterministic:
+            flags |= _lib.FLAG_DETERMINISTIC
+        with torch.cuda.device(x.device):
+            ws_bytes = _lib.bwd_workspace_bytes(N, C, H, W, B, need_x, flags)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+            stream = torch.cuda.current_stream().cuda_stream
+            _lib.warp_blend_bwd(_ptr(x), _ptr(flow), _ptr(mask), _ptr(other), _ptr(gout), _ptr(gx), _ptr(gflow),
+                                _ptr(gmask), _ptr(gother), N, C, H, W, B, x.stride(), gout.stride(), padding,
+                                flags, _ptr(ws), ws_bytes, stream)
+        return gx, gflow, gmask, gother, None, None, None
+
+
+def warp_blend(x, flow, mask=None, other=None, padding="border", deterministic=None, flags=0):
+    """Fused ``resample(x, flow) * mask`` of the reference (ops.py:187-193, generator.py:93).
+
+    x      [B,C,H,W] float32 CUDA, NCHW-contiguous or channels-last (output follows x's format);
+           B == N, or B divides N and frame n samples image n % B (the T-fold repeat of
+           motion_autoencoder.py:117-119 without materialising it).
+    flow   [N,2,H,W] displacement in pixels, channel 0 = x.
+    mask   [N,1,H,W] or None (None: plain warp, generator.py:95-96).
+    other  optional [N,C,H,W]: out = mask*warp + (1-mask)*other (not in the reference).
+    """
+    if deterministic is None:
+        deterministic = deterministic_default()
+    return WarpBlendFunction.apply(x, flow, mask, other, _PADDING[padding], bool(deterministic), int(flags))

@@ -1,0 +1,97 @@
+"""Drop-in replacements for the three free functions of the reference's ops layer
+(/root/reference/src/utils/ops.py:183-202), same names, same argument meaning:
+
+    resample(image, flow, mode='bilinear')      ops.py:187
+    grid_sample(input1, input2, mode='bilinear') ops.py:183
+    get_grid(batchsize, rows, cols, gpu_id=0)    ops.py:196
+
+`resample` no longer builds a grid on the CPU, copies it to the GPU and runs five kernels: it is
+one launch of the fused sm_100a kernel (c2m_b200.functional.warp_blend with mask=None).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from .functional import WarpBlendFunction, deterministic_default, warp_blend
+
+__all__ = ["resample", "grid_sample", "get_grid", "warp_blend"]
+
+
+def _check_mode(mode: str) -> None:
+    # every call site of the reference passes the default; ATen's other modes
+    # ('nearest', 'bicubic') are not part of this path
+    if mode != "bilinear":
+        raise NotImplementedError(f"c2m_b200: only mode='bilinear' is implemented, got {mode!r}")
+
+
+def resample(image: torch.Tensor, flow: torch.Tensor, mode: str = "bilinear") -> torch.Tensor:
+    """Backward-warp `image` [B,C,H,W] by the pixel `flow` [B,2,H,W] (channel 0 = x) with the
+    reference's exact convention: (size-1)/2 flow normalisation, align_corners=False sampling,
+    border padding (ops.py:187-193)."""
+    _check_mode(mode)
+    return warp_blend(image, flow, None)
+
+
+def grid_sample(input1: torch.Tensor, input2: torch.Tensor, mode: str = "bilinear") -> torch.Tensor:
+    """F.grid_sample(input1, input2, padding_mode='border') of ops.py:183-184: `input2` is a
+    normalised sampling grid [N,H,W,2]."""
+    _check_mode(mode)
+    if input2.dim() != 4 or input2.shape[-1] != 2:
+        raise ValueError(f"grid must be [N,H,W,2], got {tuple(input2.shape)}")
+    if tuple(input2.shape[1:3]) != tuple(input1.shape[2:]):
+        # ATen allows an output size different from the input size; no call site of the path does
+        raise NotImplementedError("c2m_b200.grid_sample: grid and input must share H and W")
+    return _GridSampleFunction.apply(input1, input2)
+
+
+class _GridSampleFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, image, grid):
+        x = image.contiguous()
+        g = grid.contiguous()  # [N,H,W,2]; the kernels take it through the `flow` slot
+        N, H, W, _ = g.shape
+        C = x.shape[1]
+        if not (x.is_cuda and g.is_cuda) or x.dtype != torch.float32 or g.dtype != torch.float32:
+            raise RuntimeError("c2m_b200.grid_sample: float32 CUDA tensors required (no CPU fallback)")
+        out = torch.empty((N, C, H, W), dtype=x.dtype, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.warp_blend_fwd(x.data_ptr(), g.data_ptr(), None, None, out.data_ptr(), N, C, H, W, x.shape[0],
+                                x.stride(), out.stride(), _lib.PAD_BORDER, _lib.FLAG_COORD_GRID,
+                                torch.cuda.current_stream().cuda_stream)
+        ctx.save_for_backward(x, g)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gout):
+        x, g = ctx.saved_tensors
+        gout = gout.contiguous()
+        N, H, W, _ = g.shape
+        C = x.shape[1]
+        need_x, need_g = ctx.needs_input_grad
+        gx = torch.empty_like(x) if need_x else None
+        gg = torch.empty_like(g) if need_g else None
+        flags = _lib.FLAG_COORD_GRID | (_lib.FLAG_DETERMINISTIC if deterministic_default() else 0)
+        with torch.cuda.device(x.device):
+            nbytes = _lib.bwd_workspace_bytes(N, C, H, W, x.shape[0], need_x, flags)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+            _lib.warp_blend_bwd(x.data_ptr(), g.data_ptr(), None, None, gout.data_ptr(),
+                                None if gx is None else gx.data_ptr(), None if gg is None else gg.data_ptr(),
+                                None, None, N, C, H, W, x.shape[0], x.stride(), gout.stride(), _lib.PAD_BORDER,
+                                flags, ws.data_ptr(), nbytes, torch.cuda.current_stream().cuda_stream)
+        return gx, gg
+
+
+def get_grid(batchsize: int, rows: int, cols: int, gpu_id=0) -> torch.Tensor:
+    """[B,2,rows,cols] base grid of ops.py:196-202, produced on the device (no CPU build, no H2D
+    copy) and bit-identical to the reference's CPU float32 linspace construction."""
+    device = gpu_id if isinstance(gpu_id, torch.device) else torch.device("cuda", int(gpu_id))
+    grid = torch.empty((batchsize, 2, rows, cols), dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        _lib.base_grid(grid.data_ptr(), batchsize, rows, cols, torch.cuda.current_stream().cuda_stream)
+    return grid
+
+
+# re-exported so `from c2m_b200.ops import *` mirrors `from utils.ops import *`
+_ = WarpBlendFunction

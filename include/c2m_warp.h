@@ -1,0 +1,106 @@
+/*
+ * c2m_warp.h -- C ABI of libc2m_warp.so: the fused flow-warp + occlusion-blend op of C2M for
+ * NVIDIA B200 (sm_100a).  Plain pointers and sizes only; no torch / C++ types cross this boundary.
+ *
+ * What each entry point replaces in the reference (PierfrancescoArdino/C2M):
+ *
+ *   c2m_warp_blend_fwd   src/utils/ops.py:187-193 `resample` (base grid :196-202 + flow
+ *                        normalisation :190 + F.grid_sample bilinear/border :183-184) followed by
+ *                        `* occlusion_map` at src/modules/generator/generator.py:93 and
+ *                        src/modules/motion_estimator/motion_autoencoder.py:125.
+ *   c2m_warp_blend_bwd   the autograd graph of the above (ATen grid_sampler_2d_backward, mul
+ *                        backward, div/cat/add backward) -- the reference has no source for it.
+ *   c2m_base_grid        src/utils/ops.py:196-202 `get_grid` (device-side, bit-identical to the
+ *                        CPU-built float32 linspace grid).
+ *
+ * The reference's own native-operator convention (its only hand-written warp,
+ * src/modules/third_party/resample2d/src/resample2d_cuda.cc:6-33) is followed where it makes
+ * sense: the caller allocates every output, tensors are borrowed for the duration of the call,
+ * work is enqueued on the stream that is passed in and the call returns without synchronising.
+ * Unlike that operator, errors are reported (return code + c2m_warp_last_error()).
+ *
+ * Conventions
+ *   - all tensors are float32 device memory on the current CUDA device;
+ *   - x / out / gout / gx / other are logical [N, C, H, W] with element strides passed explicitly
+ *     (NCHW-contiguous and channels-last have dedicated kernels, any other stride pattern runs a
+ *     generic kernel); flow is [N, 2, H, W] contiguous, channel 0 = x displacement in pixels;
+ *     mask is [N, 1, H, W] contiguous or NULL;
+ *   - `other` NULL  => out = mask * warp(x)                       (reference semantics)
+ *     `other` given => out = mask * warp(x) + (1 - mask) * other  (north-star blend, needs mask);
+ *   - x_batch: number of distinct images in x. x_batch == N (or 0) is the plain case. x_batch < N
+ *     (N % x_batch == 0) means frame n reads image n % x_batch, i.e. the T-fold repeat of
+ *     motion_autoencoder.py:117-119 without materialising the copies; gx is then [x_batch,C,H,W]
+ *     and receives the sum over the repeats;
+ *   - return 0 on success, a C2M_ERR_* code otherwise (message: c2m_warp_last_error(), thread
+ *     local).  No hidden synchronisation, no allocation, no global mutable state besides a
+ *     once-initialised driver entry point.
+ */
+#ifndef C2M_WARP_H_
+#define C2M_WARP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define C2M_API __attribute__((visibility("default")))
+#else
+#define C2M_API
+#endif
+
+#define C2M_WARP_VERSION 100
+
+/* padding (ATen GridSamplerPadding): the reference path uses border (ops.py:184); zeros is the
+ * flavour of src/modules/motion_estimator/dense_motion.py:167 */
+#define C2M_PAD_BORDER 0
+#define C2M_PAD_ZEROS 1
+
+/* flags */
+#define C2M_FLAG_DETERMINISTIC 0x1  /* bwd: bitwise run-to-run reproducible grad-input */
+#define C2M_FLAG_COORD_GRID 0x2     /* `flow` is a normalised sampling grid [N,H,W,2] (utils.grid_sample, ops.py:183); gflow has that shape too */
+#define C2M_FLAG_TRUE_DIV 0x100     /* probe only: divide by (size-1)/2 (ATen CPU) instead of * reciprocal (ATen CUDA) */
+#define C2M_FLAG_NO_FMA 0x200       /* probe only: unfused (c+1)*size-1 */
+#define C2M_FLAG_FORCE_GENERIC 0x400 /* run the stride-generic kernels (test hook) */
+#define C2M_FLAG_NO_TMA 0x800       /* stage flow/mask with plain loads instead of TMA (test hook) */
+#define C2M_FLAG_BWD_ATOMIC 0x1000  /* bwd: force the direct global-atomics scatter (test hook) */
+
+#define C2M_OK 0
+#define C2M_ERR_INVALID 1   /* bad argument (null pointer, size, stride, alignment) */
+#define C2M_ERR_CUDA 2      /* a CUDA runtime / driver call failed */
+#define C2M_ERR_WORKSPACE 3 /* workspace too small */
+
+C2M_API int c2m_warp_version(void);
+C2M_API const char* c2m_warp_last_error(void);
+
+C2M_API int c2m_warp_blend_fwd(const float* x, const float* flow, const float* mask, const float* other,
+                       float* out, int64_t N, int C, int H, int W, int64_t x_batch,
+                       const int64_t x_strides[4], const int64_t out_strides[4],
+                       int padding, int flags, void* cuda_stream);
+
+/* Any of gx / gflow / gmask / gother may be NULL (<=> ctx.needs_input_grad false).  gx is fully
+ * written by the call (zero-filled first when the scatter uses atomics); it has x's strides.
+ * gout and gother have g_strides.  workspace: c2m_warp_bwd_workspace_bytes() bytes, 256-byte
+ * aligned, contents undefined on entry and exit. */
+C2M_API int c2m_warp_blend_bwd(const float* x, const float* flow, const float* mask, const float* other,
+                       const float* gout, float* gx, float* gflow, float* gmask, float* gother,
+                       int64_t N, int C, int H, int W, int64_t x_batch,
+                       const int64_t x_strides[4], const int64_t g_strides[4],
+                       int padding, int flags, void* workspace, size_t workspace_bytes,
+                       void* cuda_stream);
+
+C2M_API size_t c2m_warp_bwd_workspace_bytes(int64_t N, int C, int H, int W, int64_t x_batch, int want_gx,
+                                    int flags);
+
+/* [N,2,H,W] base grid, bit-identical to the reference's CPU float32 construction. */
+C2M_API int c2m_base_grid(float* grid, int64_t N, int H, int W, void* cuda_stream);
+
+/* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
+C2M_API uint64_t c2m_warp_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* C2M_WARP_H_ */

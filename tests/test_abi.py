@@ -1,0 +1,97 @@
+"""CPU tests of the C-ABI boundary: the library builds, loads without a GPU, exports exactly what
+include/c2m_warp.h declares, and validates arguments before touching the device."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+from c2m_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "c2m_warp.h")
+
+
+def _declared_symbols():
+    src = open(HEADER).read()
+    return sorted(set(re.findall(r"C2M_API\s+[\w\s\*]+?\b(c2m_\w+)\s*\(", src)))
+
+
+def test_header_and_binding_agree():
+    assert _declared_symbols() == sorted(_lib.SYMBOLS)
+
+
+def test_library_loads_and_exports_every_symbol():
+    lib = _lib.load()
+    for name in _declared_symbols():
+        assert getattr(lib, name) is not None
+    assert lib.c2m_warp_version() == 100
+
+
+def test_dynamic_symbol_table_has_only_the_abi():
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = sorted(l.split()[-1] for l in out.splitlines() if " T " in l)
+    assert exported == _declared_symbols()
+
+
+def test_no_link_time_dependency_on_libcuda():
+    out = subprocess.run(["ldd", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "libcuda.so" not in out
+
+
+def test_sass_is_sm100a_and_uses_tma():
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass or "SM100a" in sass or "sm_100" in sass
+    assert "UTMALDG" in sass  # cp.async.bulk.tensor staging of the flow/mask tiles
+    assert "REDG" in sass or "RED." in sass or "ATOMG" in sass
+
+
+def test_flag_constants_match_header():
+    src = open(HEADER).read()
+    for name in ("DETERMINISTIC", "COORD_GRID", "TRUE_DIV", "NO_FMA", "FORCE_GENERIC", "NO_TMA", "BWD_ATOMIC"):
+        m = re.search(r"#define\s+C2M_FLAG_%s\s+(0x[0-9a-fA-F]+)" % name, src)
+        assert m and int(m.group(1), 16) == getattr(_lib, "FLAG_" + name)
+    assert int(re.search(r"#define\s+C2M_PAD_ZEROS\s+(\d+)", src).group(1)) == _lib.PAD_ZEROS
+
+
+def test_argument_validation_happens_before_any_device_work():
+    s = _lib.strides4((1, 1, 1, 1))
+    lib = _lib.load()
+    # negative size
+    rc = lib.c2m_warp_blend_fwd(None, None, None, None, None, -1, 1, 1, 1, 0, s, s, 0, 0, None)
+    assert rc == 1 and b"invalid sizes" in lib.c2m_warp_last_error()
+    # bad padding
+    rc = lib.c2m_warp_blend_fwd(None, None, None, None, None, 1, 1, 1, 1, 0, s, s, 7, 0, None)
+    assert rc == 1 and b"padding" in lib.c2m_warp_last_error()
+    # x_batch must divide N
+    rc = lib.c2m_warp_blend_fwd(None, None, None, None, None, 5, 1, 1, 1, 2, s, s, 0, 0, None)
+    assert rc == 1 and b"x_batch" in lib.c2m_warp_last_error()
+    # null pointers with a non-empty problem
+    rc = lib.c2m_warp_blend_fwd(None, None, None, None, None, 1, 1, 2, 2, 0, s, s, 0, 0, None)
+    assert rc == 1 and b"null" in lib.c2m_warp_last_error()
+    rc = lib.c2m_warp_blend_bwd(None, None, None, None, None, None, None, None, None, 1, 1, 2, 2, 0, s, s, 0, 0,
+                                None, 0, None)
+    assert rc == 1
+    # empty problems are a no-op, not an error (reference: empty tensors pass through grid_sample)
+    assert lib.c2m_warp_blend_fwd(None, None, None, None, None, 0, 3, 4, 4, 0, s, s, 0, 0, None) == 0
+    assert lib.c2m_warp_blend_bwd(None, None, None, None, None, None, None, None, None, 0, 3, 4, 4, 0, s, s, 0, 0,
+                                  None, 0, None) == 0
+    with pytest.raises(_lib.C2MWarpError):
+        _lib.warp_blend_fwd(None, None, None, None, None, 1, 1, 2, 2, 0, (1, 1, 1, 1), (1, 1, 1, 1), 0, 0, None)
+
+
+def test_workspace_size_contract():
+    assert _lib.bwd_workspace_bytes(4, 8, 16, 32, 4, True, 0) == 256
+    det = _lib.bwd_workspace_bytes(4, 8, 16, 32, 4, True, _lib.FLAG_DETERMINISTIC)
+    assert det == 256 + 4 * 8 * 16 * 32 * 8
+    # repeat: gx only has x_batch images
+    assert _lib.bwd_workspace_bytes(10, 8, 16, 32, 2, True, _lib.FLAG_DETERMINISTIC) == 256 + 2 * 8 * 16 * 32 * 8
+    assert _lib.bwd_workspace_bytes(4, 8, 16, 32, 4, False, _lib.FLAG_DETERMINISTIC) == 256
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_lib.C2MWarpError):
+        _lib.load()

@@ -1,0 +1,359 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C ABI
+(c2m_b200 -> ctypes -> libc2m_warp.so).  Checkers: oracle.reference_torch on the same device (the
+reference's own CUDA arithmetic), oracle.warp_numpy, and the committed golden vectors.
+
+Tolerances (BASELINE.json north_star): forward <= 1e-5, gradients <= 1e-4, both as
+max|a-b| / max|b| over the tensor.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import c2m_b200
+from c2m_b200 import _lib
+from oracle import reference_torch as rt
+from oracle import warp_numpy as wn
+
+pytestmark = pytest.mark.gpu
+
+FWD_TOL = 1e-5
+GRAD_TOL = 1e-4
+GOLD = sorted(g for g in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
+              if not g.endswith("base_grid_rows.npz"))
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda", 0)
+
+
+def rel(a, b):
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    den = b.abs().max().item() if b.numel() else 0.0
+    if a.numel() == 0:
+        return 0.0
+    num = (a - b).abs().max().item()
+    return num / den if den > 0 else num
+
+
+def make_inputs(dev, N, C, H, W, seed=0, amp=8.0, noise=1.0, oob=False, B=None):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B or N, C, H, W, generator=g)
+    ii = torch.arange(H, dtype=torch.float32).view(1, H, 1)
+    jj = torch.arange(W, dtype=torch.float32).view(1, 1, W)
+    fx = amp * torch.sin(2 * np.pi * ii / max(H / 2.0, 1.0)) * torch.cos(2 * np.pi * jj / max(W / 2.0, 1.0))
+    fy = amp * torch.cos(2 * np.pi * ii / max(H / 2.0, 1.0)) * torch.sin(2 * np.pi * jj / max(W / 2.0, 1.0))
+    flow = torch.stack([fx.expand(N, H, W), fy.expand(N, H, W)], 1) + noise * torch.randn(N, 2, H, W, generator=g)
+    if oob:
+        flow = torch.randn(N, 2, H, W, generator=g) * (W / 4.0)
+        sel = torch.rand(N, 1, H, W, generator=g) < 0.05
+        flow = torch.where(sel, torch.sign(flow) * 10.0 * W, flow)
+    mask = torch.sigmoid(torch.randn(N, 1, H, W, generator=g))
+    gout = torch.randn(N, C, H, W, generator=g)
+    return [t.to(dev) for t in (x, flow, mask, gout)]
+
+
+def run_ours(x, flow, mask, gout, other=None, need=(True, True, True), **kw):
+    x = x.detach().clone().requires_grad_(need[0])
+    flow = flow.detach().clone().requires_grad_(need[1])
+    m = None if mask is None else mask.detach().clone().requires_grad_(need[2])
+    o = None if other is None else other.detach().clone().requires_grad_(True)
+    out = c2m_b200.warp_blend(x, flow, m, o, **kw)
+    ins = [t for t in (x, flow, m, o) if t is not None and t.requires_grad]
+    grads = torch.autograd.grad(out, ins, gout) if ins else []
+    return out.detach(), list(grads)
+
+
+def run_ref(x, flow, mask, gout, other=None, need=(True, True, True), B=None):
+    x = x.detach().clone().requires_grad_(need[0])
+    flow = flow.detach().clone().requires_grad_(need[1])
+    m = None if mask is None else mask.detach().clone().requires_grad_(need[2])
+    o = None if other is None else other.detach().clone().requires_grad_(True)
+    xin = x
+    if B is not None and B != flow.shape[0]:
+        xin = x.repeat(flow.shape[0] // B, 1, 1, 1)  # t-major fold, motion_autoencoder.py:117-119
+    out = rt.warp_blend(xin, flow, m, o)
+    ins = [t for t in (x, flow, m, o) if t is not None and t.requires_grad]
+    grads = torch.autograd.grad(out, ins, gout) if ins else []
+    return out.detach(), list(grads)
+
+
+def check(ours, ref, fwd_tol=FWD_TOL, grad_tol=GRAD_TOL):
+    (o, go), (r, gr) = ours, ref
+    assert rel(o, r) <= fwd_tol, f"forward rel err {rel(o, r):.3e}"
+    assert len(go) == len(gr)
+    for k, (a, b) in enumerate(zip(go, gr)):
+        assert rel(a, b) <= grad_tol, f"grad[{k}] rel err {rel(a, b):.3e}"
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[:-4] for p in GOLD])
+def test_golden_vectors(dev, path):
+    d = np.load(path)
+    kind = str(d["kind"])
+    x = torch.from_numpy(d["x"]).to(dev).requires_grad_(True)
+    flow = torch.from_numpy(d["flow"]).to(dev).requires_grad_(True)
+    mask = torch.from_numpy(d["mask"]).to(dev).requires_grad_(True) if "mask" in d.files else None
+    if kind == "resample":
+        out = c2m_b200.warp_blend(x, flow, mask)
+    elif kind == "apply_optical":
+        out = c2m_b200.apply_optical(None, x, flow, mask)
+    else:
+        T = 1
+        out = c2m_b200.decoder_warp(x, flow.unsqueeze(2), mask.unsqueeze(2), T)
+    # goldens are the reference's CPU results: its CPU and CUDA builds differ by the reciprocal
+    # multiply, hence 1e-4 here; 1e-5 is asserted against the on-device reference
+    assert rel(out, torch.from_numpy(d["out"])) <= 1e-4
+    if "gout" in d.files:
+        ins = [x, flow] + ([mask] if mask is not None else [])
+        g = torch.autograd.grad(out, ins, torch.from_numpy(d["gout"]).to(dev))
+        assert rel(g[0], torch.from_numpy(d["gx"])) <= GRAD_TOL
+        assert rel(g[1], torch.from_numpy(d["gflow"])) <= 2e-4
+        if mask is not None:
+            assert rel(g[2], torch.from_numpy(d["gmask"])) <= GRAD_TOL
+    if kind == "resample":
+        xm = x.detach()
+        ref = rt.warp_blend(xm, flow.detach(), None if mask is None else mask.detach())
+        assert rel(out, ref) <= FWD_TOL
+        o_np, _ = wn.warp_blend_forward(d["x"], d["flow"], d["mask"] if "mask" in d.files else None, variant="cuda")
+        assert rel(out, torch.from_numpy(o_np)) <= FWD_TOL
+
+
+SHAPES = [
+    (2, 64, 32, 64), (1, 3, 64, 128), (3, 5, 17, 23), (2, 8, 7, 11), (1, 1, 1, 1), (2, 4, 1, 9), (2, 4, 9, 1),
+    (5, 64, 16, 32), (2, 256, 8, 16), (1, 512, 4, 8), (2, 32, 24, 52), (1, 16, 26, 104), (1, 6, 33, 77),
+    (4, 12, 40, 36),
+]
+
+
+@pytest.mark.parametrize("shape", SHAPES, ids=[str(s) for s in SHAPES])
+@pytest.mark.parametrize("layout", ["nchw", "nhwc"])
+def test_random_shapes_vs_device_reference(dev, shape, layout):
+    N, C, H, W = shape
+    x, flow, mask, gout = make_inputs(dev, N, C, H, W, seed=sum(shape))
+    if layout == "nhwc":
+        x = x.contiguous(memory_format=torch.channels_last)
+    ours = run_ours(x, flow, mask, gout)
+    ref = run_ref(x, flow, mask, gout)
+    check(ours, ref)
+    if layout == "nhwc" and C > 1 and H * W > 1:
+        assert ours[0].is_contiguous(memory_format=torch.channels_last)
+    # and against the numpy oracle (independent restatement, CUDA coordinate variant)
+    o_np, _ = wn.warp_blend_forward(x.cpu().numpy(), flow.cpu().numpy(), mask.cpu().numpy(), variant="cuda")
+    assert rel(ours[0], torch.from_numpy(o_np)) <= FWD_TOL
+    r = wn.warp_blend_backward(x.cpu().numpy(), flow.cpu().numpy(), mask.cpu().numpy(), gout.cpu().numpy(),
+                               variant="cuda")
+    assert rel(ours[1][0], torch.from_numpy(r["gx"])) <= GRAD_TOL
+    assert rel(ours[1][1], torch.from_numpy(r["gflow"])) <= GRAD_TOL
+    assert rel(ours[1][2], torch.from_numpy(r["gmask"])) <= GRAD_TOL
+
+
+@pytest.mark.parametrize("flags", [0, _lib.FLAG_FORCE_GENERIC, _lib.FLAG_NO_TMA, _lib.FLAG_BWD_ATOMIC],
+                         ids=["default", "generic", "no_tma", "bwd_atomic"])
+@pytest.mark.parametrize("layout", ["nchw", "nhwc"])
+def test_kernel_variants_agree(dev, flags, layout):
+    x, flow, mask, gout = make_inputs(dev, 3, 24, 40, 72, seed=5)
+    if layout == "nhwc":
+        x = x.contiguous(memory_format=torch.channels_last)
+    check(run_ours(x, flow, mask, gout, flags=flags), run_ref(x, flow, mask, gout))
+    check(run_ours(x, flow, None, gout, flags=flags), run_ref(x, flow, None, gout))
+
+
+@pytest.mark.parametrize("variant", range(0, 6))
+def test_nchw_tile_variants(dev, variant):
+    x, flow, mask, gout = make_inputs(dev, 2, 16, 48, 96, seed=6)
+    ours = run_ours(x, flow, mask, gout, flags=variant << 16)
+    check(ours, run_ref(x, flow, mask, gout))
+
+
+def test_out_of_bounds_flow_border_and_zeros(dev):
+    N, C, H, W = 2, 8, 32, 104
+    x, flow, mask, gout = make_inputs(dev, N, C, H, W, seed=7, oob=True)
+    check(run_ours(x, flow, mask, gout), run_ref(x, flow, mask, gout))
+    # zeros padding (the flavour of dense_motion.py:167) against F.grid_sample(zeros)
+    xr = x.clone().requires_grad_(True)
+    fr = flow.clone().requires_grad_(True)
+    mr = mask.clone().requires_grad_(True)
+    grid = rt.base_grid(N, H, W, dev)
+    nf = torch.cat([fr[:, 0:1] / ((W - 1.0) / 2.0), fr[:, 1:2] / ((H - 1.0) / 2.0)], 1)
+    ref = F.grid_sample(xr, (grid + nf).permute(0, 2, 3, 1), mode="bilinear", padding_mode="zeros",
+                        align_corners=False) * mr
+    gref = torch.autograd.grad(ref, [xr, fr, mr], gout)
+    check(run_ours(x, flow, mask, gout, padding="zeros"), (ref.detach(), list(gref)))
+
+
+def test_nonfinite_flow_forward(dev):
+    x, flow, mask, gout = make_inputs(dev, 1, 4, 16, 32, seed=8)
+    flow[0, 0, 3, 5] = float("nan")
+    flow[0, 1, 4, 6] = float("inf")
+    flow[0, 0, 7, 9] = float("-inf")
+    out = c2m_b200.warp_blend(x, flow, mask)
+    ref = rt.warp_blend(x, flow, mask)
+    assert torch.isfinite(out).all()
+    assert rel(out, ref) <= FWD_TOL
+    # backward stays finite and matches the reference away from the poisoned pixels
+    ours = run_ours(x, flow, mask, gout)
+    refg = run_ref(x, flow, mask, gout)
+    assert all(torch.isfinite(g).all() for g in ours[1])
+    assert rel(ours[1][0], refg[1][0]) <= GRAD_TOL
+
+
+def test_needs_input_grad_subsets(dev):
+    x, flow, mask, gout = make_inputs(dev, 2, 6, 20, 28, seed=9)
+    for need in [(True, False, False), (False, True, False), (False, False, True), (True, True, False)]:
+        check(run_ours(x, flow, mask, gout, need=need), run_ref(x, flow, mask, gout, need=need))
+
+
+def test_other_blend_extension(dev):
+    x, flow, mask, gout = make_inputs(dev, 2, 5, 12, 20, seed=10)
+    other = torch.randn_like(gout)
+    check(run_ours(x, flow, mask, gout, other=other), run_ref(x, flow, mask, gout, other=other))
+
+
+@pytest.mark.parametrize("layout", ["nchw", "nhwc"])
+def test_frame_repeat_without_materialising(dev, layout):
+    B, T, C, H, W = 2, 5, 8, 16, 32
+    x, flow, mask, gout = make_inputs(dev, B * T, C, H, W, seed=11, B=B)
+    if layout == "nhwc":
+        x = x.contiguous(memory_format=torch.channels_last)
+    check(run_ours(x, flow, mask, gout), run_ref(x, flow, mask, gout, B=B))
+
+
+@pytest.mark.parametrize("layout", ["nchw", "nhwc"])
+def test_deterministic_mode_is_bitwise_reproducible(dev, layout):
+    x, flow, mask, gout = make_inputs(dev, 2, 16, 32, 64, seed=12, oob=True)
+    if layout == "nhwc":
+        x = x.contiguous(memory_format=torch.channels_last)
+    runs = [run_ours(x, flow, mask, gout, deterministic=True) for _ in range(3)]
+    for r in runs[1:]:
+        for a, b in zip(runs[0][1], r[1]):
+            assert torch.equal(a, b)
+    check(runs[0], run_ref(x, flow, mask, gout))
+    # torch's global switch selects it too (the reference op raises under that switch)
+    torch.use_deterministic_algorithms(True)
+    try:
+        again = run_ours(x, flow, mask, gout)
+    finally:
+        torch.use_deterministic_algorithms(False)
+    assert torch.equal(again[1][0], runs[0][1][0])
+
+
+def test_drop_in_functions(dev):
+    x, flow, mask, gout = make_inputs(dev, 2, 6, 8, 16, seed=13)
+    # resample == reference resample
+    assert rel(c2m_b200.resample(x, flow), rt.resample(x, flow)) <= FWD_TOL
+    # get_grid is bit-identical to the reference's CPU construction
+    g = c2m_b200.get_grid(3, 26, 104, gpu_id=0)
+    assert torch.equal(g.cpu(), rt.base_grid(3, 26, 104, "cpu"))
+    g1 = c2m_b200.get_grid(1, 1, 1, gpu_id=0)
+    assert torch.equal(g1.cpu(), rt.base_grid(1, 1, 1, "cpu"))
+    # grid_sample with an arbitrary normalised grid
+    grid = (torch.rand(2, 8, 16, 2, device=dev) * 2.4 - 1.2).requires_grad_(True)
+    xr = x.clone().requires_grad_(True)
+    ours = c2m_b200.grid_sample(xr, grid)
+    go = torch.autograd.grad(ours, [xr, grid], gout)
+    xr2 = x.clone().requires_grad_(True)
+    grid2 = grid.detach().clone().requires_grad_(True)
+    ref = rt.grid_sample_border(xr2, grid2)
+    gr = torch.autograd.grad(ref, [xr2, grid2], gout)
+    check((ours.detach(), list(go)), (ref.detach(), list(gr)))
+    # deform_input / apply_optical with the generator's resize path (feature map at 1/8 resolution)
+    feat = torch.randn(2, 12, 4, 8, device=dev)
+    flow_full = torch.randn(2, 2, 32, 64, device=dev) * 3
+    occ_full = torch.rand(2, 1, 32, 64, device=dev)
+    assert rel(c2m_b200.deform_input(feat, flow_full), rt.deform_input(feat, flow_full)) <= FWD_TOL
+    assert rel(c2m_b200.apply_optical(None, feat, flow_full, occ_full),
+               rt.apply_optical(feat, flow_full, occ_full)) <= FWD_TOL
+    assert rel(c2m_b200.apply_optical(None, x, flow, None), rt.apply_optical(x, flow, None)) <= FWD_TOL
+
+
+def test_decoder_warp_matches_reference_fold(dev):
+    B, T, C = 2, 5, 16
+    app = torch.randn(B, C, 8, 16, device=dev, requires_grad=True)
+    motion = torch.randn(B, 2, T, 32, 64, device=dev) * 4
+    occ = torch.rand(B, 1, T, 32, 64, device=dev)
+    ours = c2m_b200.decoder_warp(app, motion, occ, T)
+    app2 = app.detach().clone().requires_grad_(True)
+    ref = rt.decoder_warp(app2, motion, occ, T)
+    assert rel(ours, ref) <= FWD_TOL
+    gout = torch.randn_like(ref)
+    assert rel(torch.autograd.grad(ours, app, gout)[0], torch.autograd.grad(ref, app2, gout)[0]) <= GRAD_TOL
+
+
+def test_empty_and_degenerate_inputs(dev):
+    for shape in [(0, 3, 4, 4), (2, 0, 4, 4)]:
+        N, C, H, W = shape
+        x = torch.zeros(N, C, H, W, device=dev, requires_grad=True)
+        flow = torch.zeros(N, 2, H, W, device=dev, requires_grad=True)
+        out = c2m_b200.warp_blend(x, flow, None)
+        assert tuple(out.shape) == shape
+        gs = torch.autograd.grad(out, [x, flow], torch.zeros_like(out), allow_unused=True)
+        assert gs[1] is None or (gs[1] == 0).all()
+
+
+def test_non_default_stream_and_noncontiguous_inputs(dev):
+    x, flow, mask, gout = make_inputs(dev, 2, 6, 16, 24, seed=14)
+    xs = torch.randn(2, 6, 16, 48, device=dev)[..., ::2]  # strided view -> wrapper densifies
+    s = torch.cuda.Stream(device=dev)
+    s.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(s):
+        ours = run_ours(xs, flow, mask, gout)
+    s.synchronize()
+    check(ours, run_ref(xs.contiguous(), flow, mask, gout))
+
+
+def test_errors_are_raised_not_swallowed(dev):
+    x, flow, mask, gout = make_inputs(dev, 2, 4, 8, 8, seed=15)
+    with pytest.raises(TypeError):
+        c2m_b200.warp_blend(x.double(), flow.double(), None)
+    with pytest.raises(ValueError):
+        c2m_b200.warp_blend(x, flow[:, :, :4], None)
+    with pytest.raises(ValueError):
+        c2m_b200.warp_blend(x, flow, mask[:1])
+    with pytest.raises(ValueError):
+        c2m_b200.warp_blend(x, flow, None, torch.zeros_like(x))
+
+
+# ------------------------------------------------------------------------------------------------
+# full-size, size-independent properties (BASELINE.json configs[1..2] shapes)
+@pytest.mark.parametrize("cfg", [(8, 64, 256, 512, False), (4, 64, 256, 832, True)], ids=["cityscapes", "kitti_oob"])
+def test_full_size_properties(dev, cfg):
+    N, C, H, W, oob = cfg
+    x, flow, mask, gout = make_inputs(dev, N, C, H, W, seed=21, oob=oob)
+    out, (gx, gflow, gmask) = run_ours(x, flow, mask, gout)
+    # (1) parity with the reference's CUDA path at full size
+    ref = run_ref(x, flow, mask, gout)
+    check((out, [gx, gflow, gmask]), ref)
+    # (2) linearity in x and mask scaling
+    x2 = torch.randn_like(x)
+    o2 = c2m_b200.warp_blend(x2, flow, mask)
+    o12 = c2m_b200.warp_blend(2 * x + 3 * x2, flow, mask)
+    assert rel(o12, 2 * out + 3 * o2) <= 1e-5
+    assert rel(c2m_b200.warp_blend(x, flow, 0.5 * mask), 0.5 * out) <= 1e-6
+    # (3) adjointness: <gout, out(x)> == <gx, x> (the scatter is the transpose of the gather)
+    lhs = (gout.double() * out.double()).sum().item()
+    rhs = (gx.double() * x.double()).sum().item()
+    assert abs(lhs - rhs) <= 1e-5 * max(abs(lhs), 1.0) + 1e-3
+    # (4) checksum of the scatter: sum(gx) == sum_pixels g * (sum of in-bounds weights == 1 for border)
+    tot = gx.double().sum().item()
+    exp = (gout.double() * mask.double()).sum().item()
+    assert abs(tot - exp) <= 1e-6 * gout.numel() ** 0.5 * 10 + 1e-5 * abs(exp)
+    # (5) grad-mask identity: gmask == sum_c gout * warp(x) with mask == 1
+    warped = c2m_b200.warp_blend(x, flow, None)
+    assert rel(gmask, (gout * warped).sum(1, keepdim=True)) <= GRAD_TOL
+    # (6) NHWC path gives the same numbers
+    xl = x.contiguous(memory_format=torch.channels_last)
+    out_l, (gx_l, gflow_l, gmask_l) = run_ours(xl, flow, mask, gout)
+    assert rel(out_l, out) <= 1e-6
+    assert rel(gx_l, gx) <= GRAD_TOL and rel(gflow_l, gflow) <= GRAD_TOL and rel(gmask_l, gmask) <= GRAD_TOL
+    # (7) deterministic mode: reproducible bits, same values within tolerance
+    d1 = run_ours(x, flow, mask, gout, deterministic=True)[1][0]
+    d2 = run_ours(x, flow, mask, gout, deterministic=True)[1][0]
+    assert torch.equal(d1, d2)
+    assert rel(d1, gx) <= GRAD_TOL
