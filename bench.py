@@ -46,7 +46,8 @@ def synth(N, C, H, W, oob, seed, device, pin=False):
     two_pi = 6.283185307179586
     fx = 8.0 * torch.sin(two_pi * ii / (H / 2.0)) * torch.cos(two_pi * jj / (W / 2.0))
     fy = 8.0 * torch.cos(two_pi * ii / (H / 2.0)) * torch.sin(two_pi * jj / (W / 2.0))
-    flow = torch.stack([fx.expand(N, H, W), fy.expand(N, H, W)], 1) + torch.randn(N, 2, H, W, generator=g)
+    noise = float(os.environ.get("C2M_BENCH_FLOW_NOISE", "1.0"))  # px, SURVEY.md 8d uses 1.0
+    flow = torch.stack([fx.expand(N, H, W), fy.expand(N, H, W)], 1) + noise * torch.randn(N, 2, H, W, generator=g)
     if oob:
         flow = torch.randn(N, 2, H, W, generator=g) * (W / 4.0)
         sel = torch.rand(N, 1, H, W, generator=g) < 0.05

@@ -33,6 +33,15 @@ int sm_count() {
   return cached;
 }
 
+int resident_ctas(const void* kernel, int threads) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1) {
+    (void)cudaGetLastError();
+    per_sm = 1;
+  }
+  return per_sm * sm_count();
+}
+
 // cuTensorMapEncodeTiled is a driver-API symbol; it is resolved at run time so that the library
 // has no link-time dependency on libcuda (it must load on a machine without a GPU driver).
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

@@ -57,6 +57,10 @@ struct BwdParams {
   long long* acc64;         // fixed-point accumulator, same element order as gx
   const unsigned* maxbits;  // bit pattern of max|gout*mask|
   int count_log2;           // ceil(log2(max contributions per destination))
+  // gather-form backward (contributor lists built by bin_kernel)
+  int* cnt;                 // [x_batch*H*W] contributions seen per destination pixel
+  void* entries;            // [x_batch*H*W][kListCap] ListEntry
+  unsigned char* ovf;       // [N*H*W] bit k: corner k of this output pixel did not fit its list
 };
 
 // Per-pixel sampling geometry, shared by forward and backward.
@@ -188,18 +192,110 @@ __device__ __forceinline__ void st_stream(float4* p, float4 v) { __stcs(p, v); }
 __device__ __forceinline__ float ld_stream(const float* p) { return __ldcs(p); }
 __device__ __forceinline__ float4 ld_stream(const float4* p) { return __ldcs(p); }
 
+// Read-only 128-bit load as a volatile asm statement: the compiler keeps a run of these together
+// (it otherwise interleaves loads with their first uses and leaves only two in flight), which is
+// what gives the gather kernels their memory-level parallelism.
+__device__ __forceinline__ float4 ldg_batch(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float ldg_batch(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Tile walk shared by the layout-specialised kernels: persistent CTAs step through (n, tile_y,
+// tile_x) work items; the tile's two flow planes and its mask plane are staged in shared memory
+// by TMA one tile ahead (double buffered, one mbarrier per buffer).
+// ---------------------------------------------------------------------------------------------
+template <int TH, int TW>
+struct TileSmem {
+  alignas(128) float flow[2][2][TH][TW];
+  alignas(128) float mask[2][TH][TW];
+  alignas(8) uint64_t bar[2];
+};
+
+template <int TH, int TW, bool HAS_MASK>
+__device__ __forceinline__ void issue_tile(TileSmem<TH, TW>& s, const CUtensorMap* tmf, const CUtensorMap* tmm,
+                                           int t, int tiles_x, int tiles_y, int b) {
+  const int bx = t % tiles_x;
+  const int r = t / tiles_x;
+  const int by = r % tiles_y;
+  const int n = r / tiles_y;
+  constexpr uint32_t bytes = (HAS_MASK ? 3u : 2u) * TH * TW * sizeof(float);
+  mbar_expect_tx(&s.bar[b], bytes);
+  tma_load_3d(&s.flow[b][0][0][0], tmf, &s.bar[b], bx * TW, by * TH, n * 2);
+  if (HAS_MASK) tma_load_3d(&s.mask[b][0][0], tmm, &s.bar[b], bx * TW, by * TH, n);
+}
+
+template <int TH, int TW, bool HAS_MASK>
+__device__ __forceinline__ void tile_pipeline_init(TileSmem<TH, TW>& s, const CUtensorMap* tmf,
+                                                   const CUtensorMap* tmm, int first_tile, int total, int tiles_x,
+                                                   int tiles_y) {
+  if (threadIdx.x == 0) {
+    mbar_init(&s.bar[0], 1);
+    mbar_init(&s.bar[1], 1);
+    mbar_fence_init();
+    tma_prefetch_desc(tmf);
+    if (HAS_MASK) tma_prefetch_desc(tmm);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && first_tile < total) issue_tile<TH, TW, HAS_MASK>(s, tmf, tmm, first_tile, tiles_x, tiles_y, 0);
+}
+
+// Per-pixel geometry of one tile, computed once by a thread-per-pixel pass and then read
+// (broadcast) by the lanes that move a pixel's channels.
+template <int TP>
+struct TileGeo {
+  alignas(16) int4 off[TP];    // pixel offsets (y*W+x) of nw, ne, sw, se, clamped into the image
+  alignas(16) float4 w[TP];    // bilinear weights nw, ne, sw, se
+  alignas(16) float4 aux[TP];  // ax, ay, gmx, gmy (backward only)
+  float m[TP];                 // occlusion mask value (1 when there is no mask)
+  int ok[TP];                  // bit k set <=> corner k is inside the image; bit 4 <=> pixel inside the image
+};
+
+template <int TP>
+__device__ __forceinline__ void store_geo(TileGeo<TP>& tg, int t, const Geo& g, float m, int W, bool live) {
+  tg.off[t] = make_int4(g.y0 * W + g.x0, g.y0 * W + g.x1, g.y1 * W + g.x0, g.y1 * W + g.x1);
+  tg.w[t] = make_float4(g.wnw, g.wne, g.wsw, g.wse);
+  tg.aux[t] = make_float4(g.ax, g.ay, g.gmx, g.gmy);
+  tg.m[t] = m;
+  tg.ok[t] = live ? ((int)g.oknw | ((int)g.okne << 1) | ((int)g.oksw << 2) | ((int)g.okse << 3) | 16) : 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 enum Layout { LAYOUT_NCHW = 0, LAYOUT_NHWC = 1, LAYOUT_OTHER = 2 };
 
+// Gather-form backward: contributor lists (one per destination pixel of grad-input)
+constexpr int kListCap = 8;  // in-line entries per destination; the tail goes through atomics
+struct ListEntry {
+  int src;    // source (output) pixel index n*H*W + i*W + j
+  float w;    // bilinear weight * mask
+};
+
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 int sm_count();
+// Number of CTAs of `kernel` (static shared memory only) that are resident on the whole device at once:
+// the grid size of a persistent launch.
+int resident_ctas(const void* kernel, int threads);
 // Encodes a [planes, H, W] float32 tensor map with box (box_w, box_h, box_p); returns false when
 // the tensor does not satisfy TMA's alignment rules (caller falls back to plain loads).
 bool make_tensor_map_3d(CUtensorMap* tm, const float* base, int W, int H, int64_t planes, int box_w, int box_h,
                         int box_p);
+
+struct TileMaps {
+  CUtensorMap flow, mask;
+  bool ok;  // false: alignment rules not met (or C2M_FLAG_NO_TMA) -> kernels use plain loads
+};
+TileMaps make_tile_maps(const Dims& d, const float* flow, const float* mask, int TH, int TW);
 
 int launch_fwd(const FwdParams& p, Layout lx, Layout lo, cudaStream_t st);
 int launch_bwd(const BwdParams& p, Layout lx, Layout lg, void* workspace, size_t workspace_bytes, cudaStream_t st);

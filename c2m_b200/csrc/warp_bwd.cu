@@ -121,12 +121,18 @@ __global__ void __launch_bounds__(256) fix2float_kernel(const long long* acc, fl
 }
 
 // ---------------------------------------------------------------------------------------------
+size_t gather_workspace_bytes(int64_t N, int H, int W, int64_t x_batch);
+bool gather_supported(const BwdParams& p, Layout lx, Layout lg);
+int launch_bwd_gather(const BwdParams& pin, Layout lx, void* workspace, size_t workspace_bytes, cudaStream_t st);
+
 size_t bwd_workspace_bytes(int64_t N, int C, int H, int W, int64_t x_batch, int want_gx, int flags) {
-  (void)N;
   size_t b = 256;
-  if (want_gx && (flags & C2M_FLAG_DETERMINISTIC)) {
-    const int64_t xb = x_batch > 0 ? x_batch : N;
-    b += (size_t)xb * C * H * W * sizeof(long long);
+  if (!want_gx) return b;
+  const int64_t xb = x_batch > 0 ? x_batch : N;
+  if (flags & C2M_FLAG_DETERMINISTIC) {
+    b += (size_t)xb * C * H * W * sizeof(long long);  // fixed-point accumulator
+  } else if (!(flags & (C2M_FLAG_BWD_ATOMIC | C2M_FLAG_FORCE_GENERIC | C2M_FLAG_COORD_GRID))) {
+    b += gather_workspace_bytes(N, H, W, xb);  // contributor lists
   }
   return b;
 }
@@ -138,8 +144,9 @@ static int grid_for(int64_t total) {
 }
 
 int launch_bwd(const BwdParams& pin, Layout lx, Layout lg, void* workspace, size_t workspace_bytes, cudaStream_t st) {
-  (void)lx;
-  (void)lg;
+  if (gather_supported(pin, lx, lg))
+    return launch_bwd_gather(pin, lx, reinterpret_cast<char*>(workspace) + 256,
+                             workspace_bytes >= 256 ? workspace_bytes - 256 : 0, st);
   BwdParams p = pin;
   const Dims& d = p.d;
   const int64_t total = (int64_t)d.N * d.H * d.W;

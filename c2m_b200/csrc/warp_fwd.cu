@@ -9,8 +9,10 @@
 //                       (cp.async.bulk.tensor.3d, double buffered, mbarrier-signalled) one tile
 //                       ahead; one thread per pixel, channel loop unrolled for memory-level
 //                       parallelism; stores are 128-byte coalesced along W.
-//   fwd_nhwc_kernel     channels-last; same tile walk and TMA staging; LP lanes per pixel, each
-//                       moving float4 channel groups: four 128-bit corner loads + one 128-bit store.
+//   fwd_nhwc_kernel     channels-last; same tile walk and TMA staging; a thread-per-pixel pass
+//                       writes the tile's geometry to shared memory, then LP lanes per pixel move
+//                       float4 channel groups: four 128-bit corner loads + one 128-bit store, every
+//                       access a full 16-byte-per-lane coalesced segment whatever the flow does.
 #include "common.cuh"
 
 namespace c2m {
@@ -52,33 +54,10 @@ __global__ void __launch_bounds__(256) fwd_generic_kernel(const FwdParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Tile walker shared by the NCHW and NHWC kernels: stages flow (2 planes) and mask (1 plane) of
-// tile t into buffer b.
-template <int TH, int TW>
-struct TileSmem {
-  alignas(128) float flow[2][2][TH][TW];
-  alignas(128) float mask[2][TH][TW];
-  alignas(8) uint64_t bar[2];
-};
-
-template <int TH, int TW, bool HAS_MASK>
-__device__ __forceinline__ void issue_tile(TileSmem<TH, TW>& s, const CUtensorMap* tmf, const CUtensorMap* tmm,
-                                           int t, int tiles_x, int tiles_y, int b) {
-  const int bx = t % tiles_x;
-  const int r = t / tiles_x;
-  const int by = r % tiles_y;
-  const int n = r / tiles_y;
-  constexpr uint32_t bytes = (HAS_MASK ? 3u : 2u) * TH * TW * sizeof(float);
-  mbar_expect_tx(&s.bar[b], bytes);
-  tma_load_3d(&s.flow[b][0][0][0], tmf, &s.bar[b], bx * TW, by * TH, n * 2);
-  if (HAS_MASK) tma_load_3d(&s.mask[b][0][0], tmm, &s.bar[b], bx * TW, by * TH, n);
-}
-
-// ---------------------------------------------------------------------------------------------
 template <int TH, int TW, bool HAS_MASK, bool USE_TMA, int UNROLL>
-__global__ void __launch_bounds__(TH* TW, (TH * TW <= 256) ? 768 / (TH * TW) : 2) fwd_nchw_kernel(const __grid_constant__ FwdParams p,
-                                                          const __grid_constant__ CUtensorMap tm_flow,
-                                                          const __grid_constant__ CUtensorMap tm_mask) {
+__global__ void __launch_bounds__(TH* TW, (TH * TW <= 256) ? 768 / (TH * TW) : 2)
+    fwd_nchw_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ CUtensorMap tm_flow,
+                    const __grid_constant__ CUtensorMap tm_mask) {
   __shared__ TileSmem<TH, TW> s;
   const Dims& d = p.d;
   const int tid = threadIdx.x;
@@ -89,18 +68,7 @@ __global__ void __launch_bounds__(TH* TW, (TH * TW <= 256) ? 768 / (TH * TW) : 2
   const int nc = min(p.cchunk, d.C - c0);
   const int HW = d.H * d.W;
 
-  if (USE_TMA) {
-    if (tid == 0) {
-      mbar_init(&s.bar[0], 1);
-      mbar_init(&s.bar[1], 1);
-      mbar_fence_init();
-      tma_prefetch_desc(&tm_flow);
-      if (HAS_MASK) tma_prefetch_desc(&tm_mask);
-    }
-    __syncthreads();
-    if (tid == 0 && (int)blockIdx.x < total)
-      issue_tile<TH, TW, HAS_MASK>(s, &tm_flow, &tm_mask, blockIdx.x, tiles_x, tiles_y, 0);
-  }
+  if (USE_TMA) tile_pipeline_init<TH, TW, HAS_MASK>(s, &tm_flow, &tm_mask, blockIdx.x, total, tiles_x, tiles_y);
   int buf = 0;
   uint32_t phases = 0;
   for (int t = blockIdx.x; t < total; t += gridDim.x) {
@@ -128,13 +96,11 @@ __global__ void __launch_bounds__(TH* TW, (TH * TW <= 256) ? 768 / (TH * TW) : 2
     if (live) {
       Geo g;
       make_geo<false>(d, fx, fy, i, j, g);
-      const int onw = g.y0 * d.W + g.x0, one = g.y0 * d.W + g.x1;
-      const int osw = g.y1 * d.W + g.x0, ose = g.y1 * d.W + g.x1;
       const float* xc = p.x + ((int64_t)(n % d.x_batch) * d.C + c0) * HW;
-      const float* pnw = xc + onw;
-      const float* pne = xc + one;
-      const float* psw = xc + osw;
-      const float* pse = xc + ose;
+      const float* pnw = xc + (g.y0 * d.W + g.x0);
+      const float* pne = xc + (g.y0 * d.W + g.x1);
+      const float* psw = xc + (g.y1 * d.W + g.x0);
+      const float* pse = xc + (g.y1 * d.W + g.x1);
       float* oc = p.out + ((int64_t)n * d.C + c0) * HW + i * d.W + j;
 #pragma unroll UNROLL
       for (int c = 0; c < nc; ++c) {
@@ -164,17 +130,21 @@ __global__ void __launch_bounds__(TH* TW, (TH * TW <= 256) ? 768 / (TH * TW) : 2
 }
 
 // ---------------------------------------------------------------------------------------------
-// channels-last: LP lanes cooperate on one pixel, lane q handles float4 groups q, q+LP, ...
+// channels-last.  NT threads, tile of TH x TW = NT pixels.  Pass 1: thread t computes the geometry
+// of tile pixel t.  Pass 2: LP consecutive lanes own one pixel at a time and stream its C/4 float4
+// channel groups.
 template <int TH, int TW, int LP, bool HAS_MASK, bool USE_TMA>
-__global__ void __launch_bounds__(256) fwd_nhwc_kernel(const __grid_constant__ FwdParams p,
-                                                       const __grid_constant__ CUtensorMap tm_flow,
-                                                       const __grid_constant__ CUtensorMap tm_mask) {
+__global__ void __launch_bounds__(TH* TW) fwd_nhwc_kernel(const __grid_constant__ FwdParams p,
+                                                          const __grid_constant__ CUtensorMap tm_flow,
+                                                          const __grid_constant__ CUtensorMap tm_mask) {
+  constexpr int NT = TH * TW;
+  constexpr int GROUPS = NT / LP;  // pixels in flight per pass
   __shared__ TileSmem<TH, TW> s;
-  constexpr int NT = 256;
-  constexpr int PIX_PER_PASS = NT / LP;
+  __shared__ TileGeo<NT> tg;
   const Dims& d = p.d;
   const int tid = threadIdx.x;
-  const int lane_q = tid % LP, pix0 = tid / LP;
+  const int lane_q = tid % LP, grp = tid / LP;
+  const int tx = tid % TW, ty = tid / TW;
   const int tiles_x = (d.W + TW - 1) / TW, tiles_y = (d.H + TH - 1) / TH;
   const int total = d.N * tiles_y * tiles_x;
   const int HW = d.H * d.W;
@@ -182,18 +152,7 @@ __global__ void __launch_bounds__(256) fwd_nhwc_kernel(const __grid_constant__ F
   const int q0 = blockIdx.y * p.cchunk;  // cchunk counted in float4 groups here
   const int q1 = min(C4, q0 + p.cchunk);
 
-  if (USE_TMA) {
-    if (tid == 0) {
-      mbar_init(&s.bar[0], 1);
-      mbar_init(&s.bar[1], 1);
-      mbar_fence_init();
-      tma_prefetch_desc(&tm_flow);
-      if (HAS_MASK) tma_prefetch_desc(&tm_mask);
-    }
-    __syncthreads();
-    if (tid == 0 && (int)blockIdx.x < total)
-      issue_tile<TH, TW, HAS_MASK>(s, &tm_flow, &tm_mask, blockIdx.x, tiles_x, tiles_y, 0);
-  }
+  if (USE_TMA) tile_pipeline_init<TH, TW, HAS_MASK>(s, &tm_flow, &tm_mask, blockIdx.x, total, tiles_x, tiles_y);
   int buf = 0;
   uint32_t phases = 0;
   for (int t = blockIdx.x; t < total; t += gridDim.x) {
@@ -201,75 +160,94 @@ __global__ void __launch_bounds__(256) fwd_nhwc_kernel(const __grid_constant__ F
     const int r = t / tiles_x;
     const int by = r % tiles_y;
     const int n = r / tiles_y;
-    if (USE_TMA) {
-      const int tn = t + gridDim.x;
-      if (tid == 0 && tn < total) issue_tile<TH, TW, HAS_MASK>(s, &tm_flow, &tm_mask, tn, tiles_x, tiles_y, buf ^ 1);
-      mbar_wait(&s.bar[buf], (phases >> buf) & 1u);
-      phases ^= 1u << buf;
-    }
-    const float4* xb = reinterpret_cast<const float4*>(p.x + (int64_t)(n % d.x_batch) * HW * d.C);
-    float4* ob = reinterpret_cast<float4*>(p.out + (int64_t)n * HW * d.C);
-#pragma unroll 2
-    for (int pp = pix0; pp < TH * TW; pp += PIX_PER_PASS) {
-      const int ty = pp / TW, tx = pp % TW;
+    {  // pass 1
       const int i = by * TH + ty, j = bx * TW + tx;
-      if ((i >= d.H) | (j >= d.W)) continue;
-      float fx, fy, m = 1.f;
+      const bool live = (i < d.H) & (j < d.W);
+      float fx = 0.f, fy = 0.f, m = 1.f;
       if (USE_TMA) {
+        const int tn = t + gridDim.x;
+        if (tid == 0 && tn < total) issue_tile<TH, TW, HAS_MASK>(s, &tm_flow, &tm_mask, tn, tiles_x, tiles_y, buf ^ 1);
+        mbar_wait(&s.bar[buf], (phases >> buf) & 1u);
+        phases ^= 1u << buf;
         fx = s.flow[buf][0][ty][tx];
         fy = s.flow[buf][1][ty][tx];
         if (HAS_MASK) m = s.mask[buf][ty][tx];
-      } else {
+        buf ^= 1;
+      } else if (live) {
         const float* fl = p.flow + (int64_t)n * 2 * HW + i * d.W + j;
         fx = __ldg(fl);
         fy = __ldg(fl + HW);
         if (HAS_MASK) m = __ldg(p.mask + (int64_t)n * HW + i * d.W + j);
       }
       Geo g;
-      make_geo<false>(d, fx, fy, i, j, g);
-      const float4* pnw = xb + (int64_t)(g.y0 * d.W + g.x0) * C4;
-      const float4* pne = xb + (int64_t)(g.y0 * d.W + g.x1) * C4;
-      const float4* psw = xb + (int64_t)(g.y1 * d.W + g.x0) * C4;
-      const float4* pse = xb + (int64_t)(g.y1 * d.W + g.x1) * C4;
-      float4* po = ob + (int64_t)(i * d.W + j) * C4;
-      const float wnw = g.oknw ? g.wnw : 0.f, wne = g.okne ? g.wne : 0.f;
-      const float wsw = g.oksw ? g.wsw : 0.f, wse = g.okse ? g.wse : 0.f;
-#pragma unroll 2
-      for (int q = q0 + lane_q; q < q1; q += LP) {
-        float4 a = __ldg(pnw + q), b = __ldg(pne + q), c = __ldg(psw + q), e = __ldg(pse + q);
-        if (!g.oknw) a = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (!g.okne) b = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (!g.oksw) c = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (!g.okse) e = make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 o;
-        o.x = fmaf(e.x, wse, fmaf(c.x, wsw, fmaf(b.x, wne, a.x * wnw)));
-        o.y = fmaf(e.y, wse, fmaf(c.y, wsw, fmaf(b.y, wne, a.y * wnw)));
-        o.z = fmaf(e.z, wse, fmaf(c.z, wsw, fmaf(b.z, wne, a.z * wnw)));
-        o.w = fmaf(e.w, wse, fmaf(c.w, wsw, fmaf(b.w, wne, a.w * wnw)));
-        if (HAS_MASK) {
-          o.x = __fmul_rn(o.x, m);
-          o.y = __fmul_rn(o.y, m);
-          o.z = __fmul_rn(o.z, m);
-          o.w = __fmul_rn(o.w, m);
+      make_geo<false>(d, fx, fy, min(i, d.H - 1), min(j, d.W - 1), g);
+      store_geo(tg, tid, g, m, d.W, live);
+    }
+    __syncthreads();
+    const float4* xb = reinterpret_cast<const float4*>(p.x) + (int64_t)(n % d.x_batch) * HW * C4;
+    float4* ob = reinterpret_cast<float4*>(p.out) + (int64_t)n * HW * C4;
+    for (int pp = grp; pp < NT; pp += GROUPS) {
+      const int ok = tg.ok[pp];
+      if (!(ok & 16)) continue;
+      const int4 off = tg.off[pp];
+      const float4 w = tg.w[pp];
+      const float m = tg.m[pp];
+      const int pix = (by * TH + pp / TW) * d.W + bx * TW + pp % TW;
+      const float4* pnw = xb + (int64_t)off.x * C4;
+      const float4* pne = xb + (int64_t)off.y * C4;
+      const float4* psw = xb + (int64_t)off.z * C4;
+      const float4* pse = xb + (int64_t)off.w * C4;
+      float4* po = ob + (int64_t)pix * C4;
+      for (int q = q0 + lane_q; q < q1; q += 2 * LP) {
+        const bool two = (q + LP) < q1;
+        // all corner loads of both channel groups are issued before the first use
+        float4 a0 = ldg_batch(pnw + q), b0 = ldg_batch(pne + q), c0 = ldg_batch(psw + q), e0 = ldg_batch(pse + q);
+        float4 a1 = a0, b1 = b0, c1 = c0, e1 = e0;
+        if (two) {
+          a1 = ldg_batch(pnw + q + LP);
+          b1 = ldg_batch(pne + q + LP);
+          c1 = ldg_batch(psw + q + LP);
+          e1 = ldg_batch(pse + q + LP);
         }
-        st_stream(po + q, o);
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!(ok & 1)) a0 = a1 = z;
+        if (!(ok & 2)) b0 = b1 = z;
+        if (!(ok & 4)) c0 = c1 = z;
+        if (!(ok & 8)) e0 = e1 = z;
+#define C2M_BLEND(O, A, B, C, E)                                       \
+  O.x = fmaf(E.x, w.w, fmaf(C.x, w.z, fmaf(B.x, w.y, A.x * w.x)));     \
+  O.y = fmaf(E.y, w.w, fmaf(C.y, w.z, fmaf(B.y, w.y, A.y * w.x)));     \
+  O.z = fmaf(E.z, w.w, fmaf(C.z, w.z, fmaf(B.z, w.y, A.z * w.x)));     \
+  O.w = fmaf(E.w, w.w, fmaf(C.w, w.z, fmaf(B.w, w.y, A.w * w.x)));     \
+  if (HAS_MASK) {                                                      \
+    O.x = __fmul_rn(O.x, m);                                           \
+    O.y = __fmul_rn(O.y, m);                                           \
+    O.z = __fmul_rn(O.z, m);                                           \
+    O.w = __fmul_rn(O.w, m);                                           \
+  }
+        float4 o0, o1;
+        C2M_BLEND(o0, a0, b0, c0, e0)
+        st_stream(po + q, o0);
+        if (two) {
+          C2M_BLEND(o1, a1, b1, c1, e1)
+          st_stream(po + q + LP, o1);
+        }
+#undef C2M_BLEND
       }
     }
-    if (USE_TMA) {
-      __syncthreads();
-      buf ^= 1;
-    }
+    __syncthreads();  // geometry of this tile fully consumed before the next pass 1 overwrites it
   }
 }
 
 // ---------------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------------
-static int pick_grid_x(int total_tiles, int ctas_per_sm, int ysplit) {
-  const int cap = sm_count() * ctas_per_sm;
-  int gx = cap / ysplit;
-  if (gx < 1) gx = 1;
-  return total_tiles < gx ? total_tiles : gx;
+TileMaps make_tile_maps(const Dims& d, const float* flow, const float* mask, int TH, int TW) {
+  TileMaps m;
+  memset(&m, 0, sizeof(m));
+  m.ok = !(d.flags & C2M_FLAG_NO_TMA) && make_tensor_map_3d(&m.flow, flow, d.W, d.H, (int64_t)d.N * 2, TW, TH, 2);
+  if (m.ok && mask) m.ok = make_tensor_map_3d(&m.mask, mask, d.W, d.H, d.N, TW, TH, 1);
+  return m;
 }
 
 template <int TH, int TW, int UNROLL>
@@ -282,20 +260,19 @@ static int launch_nchw_t(FwdParams p, cudaStream_t st) {
   while (tiles * ysplit < want && (d.C / (ysplit * 2)) >= 8) ysplit *= 2;
   p.cchunk = (d.C + ysplit - 1) / ysplit;
   ysplit = (d.C + p.cchunk - 1) / p.cchunk;
-  CUtensorMap tmf, tmm;
-  memset(&tmf, 0, sizeof(tmf));
-  memset(&tmm, 0, sizeof(tmm));
-  bool tma = !(d.flags & C2M_FLAG_NO_TMA) && make_tensor_map_3d(&tmf, p.flow, d.W, d.H, (int64_t)d.N * 2, TW, TH, 2);
-  if (tma && p.mask) tma = make_tensor_map_3d(&tmm, p.mask, d.W, d.H, d.N, TW, TH, 1);
+  const TileMaps tm = make_tile_maps(d, p.flow, p.mask, TH, TW);
   constexpr int NT = TH * TW;
-  const int per_sm = 2048 / NT;
-  dim3 grid(pick_grid_x(tiles, per_sm, ysplit), ysplit);
-#define C2M_LAUNCH(MASK, TMA) \
-  fwd_nchw_kernel<TH, TW, MASK, TMA, UNROLL><<<grid, NT, 0, st>>>(p, tmf, tmm)
+#define C2M_LAUNCH(MASK, TMA)                                                                  \
+  do {                                                                                            \
+    auto kfn = fwd_nchw_kernel<TH, TW, MASK, TMA, UNROLL>;                                     \
+    int cap = resident_ctas(reinterpret_cast<const void*>(kfn), NT) / ysplit;                  \
+    if (cap < 1) cap = 1;                                                                      \
+    kfn<<<dim3(tiles < cap ? tiles : cap, ysplit), NT, 0, st>>>(p, tm.flow, tm.mask);          \
+  } while (0)
   if (p.mask) {
-    if (tma) C2M_LAUNCH(true, true); else C2M_LAUNCH(true, false);
+    if (tm.ok) C2M_LAUNCH(true, true); else C2M_LAUNCH(true, false);
   } else {
-    if (tma) C2M_LAUNCH(false, true); else C2M_LAUNCH(false, false);
+    if (tm.ok) C2M_LAUNCH(false, true); else C2M_LAUNCH(false, false);
   }
 #undef C2M_LAUNCH
   count_launch();
@@ -304,7 +281,7 @@ static int launch_nchw_t(FwdParams p, cudaStream_t st) {
 
 template <int LP>
 static int launch_nhwc_t(FwdParams p, cudaStream_t st) {
-  constexpr int TH = 4, TW = 32;
+  constexpr int TH = 8, TW = 32;
   const Dims& d = p.d;
   const int tiles = d.N * ((d.H + TH - 1) / TH) * ((d.W + TW - 1) / TW);
   const int C4 = d.C / 4;
@@ -313,17 +290,18 @@ static int launch_nhwc_t(FwdParams p, cudaStream_t st) {
   while (tiles * ysplit < want && (C4 / (ysplit * 2)) >= LP) ysplit *= 2;
   p.cchunk = (C4 + ysplit - 1) / ysplit;
   ysplit = (C4 + p.cchunk - 1) / p.cchunk;
-  CUtensorMap tmf, tmm;
-  memset(&tmf, 0, sizeof(tmf));
-  memset(&tmm, 0, sizeof(tmm));
-  bool tma = !(d.flags & C2M_FLAG_NO_TMA) && make_tensor_map_3d(&tmf, p.flow, d.W, d.H, (int64_t)d.N * 2, TW, TH, 2);
-  if (tma && p.mask) tma = make_tensor_map_3d(&tmm, p.mask, d.W, d.H, d.N, TW, TH, 1);
-  dim3 grid(pick_grid_x(tiles, 8, ysplit), ysplit);
-#define C2M_LAUNCH(MASK, TMA) fwd_nhwc_kernel<TH, TW, LP, MASK, TMA><<<grid, 256, 0, st>>>(p, tmf, tmm)
+  const TileMaps tm = make_tile_maps(d, p.flow, p.mask, TH, TW);
+#define C2M_LAUNCH(MASK, TMA)                                                                  \
+  do {                                                                                            \
+    auto kfn = fwd_nhwc_kernel<TH, TW, LP, MASK, TMA>;                                         \
+    int cap = resident_ctas(reinterpret_cast<const void*>(kfn), TH * TW) / ysplit;             \
+    if (cap < 1) cap = 1;                                                                      \
+    kfn<<<dim3(tiles < cap ? tiles : cap, ysplit), TH * TW, 0, st>>>(p, tm.flow, tm.mask);     \
+  } while (0)
   if (p.mask) {
-    if (tma) C2M_LAUNCH(true, true); else C2M_LAUNCH(true, false);
+    if (tm.ok) C2M_LAUNCH(true, true); else C2M_LAUNCH(true, false);
   } else {
-    if (tma) C2M_LAUNCH(false, true); else C2M_LAUNCH(false, false);
+    if (tm.ok) C2M_LAUNCH(false, true); else C2M_LAUNCH(false, false);
   }
 #undef C2M_LAUNCH
   count_launch();
@@ -332,22 +310,21 @@ static int launch_nhwc_t(FwdParams p, cudaStream_t st) {
 
 int launch_fwd(const FwdParams& p, Layout lx, Layout lo, cudaStream_t st) {
   const Dims& d = p.d;
-  const bool generic = (d.flags & (C2M_FLAG_FORCE_GENERIC | C2M_FLAG_COORD_GRID)) || p.other != nullptr || lx != lo || lx == LAYOUT_OTHER ||
-                       (int64_t)d.H * d.W >= (1ll << 30);
+  const bool generic = (d.flags & (C2M_FLAG_FORCE_GENERIC | C2M_FLAG_COORD_GRID)) || p.other != nullptr || lx != lo ||
+                       lx == LAYOUT_OTHER || (int64_t)d.H * d.W >= (1ll << 30);
   if (!generic && lx == LAYOUT_NCHW) {
     const int variant = (d.flags >> 16) & 0xf;  // tuning hook (bench sweeps); 0 = default
     switch (variant) {
       case 1: return launch_nchw_t<4, 64, 8>(p, st);
-      case 2: return launch_nchw_t<8, 64, 8>(p, st);
+      case 2: return launch_nchw_t<8, 32, 8>(p, st);
       case 3: return launch_nchw_t<16, 32, 8>(p, st);
       case 4: return launch_nchw_t<8, 32, 4>(p, st);
       case 5: return launch_nchw_t<4, 32, 8>(p, st);
-      default: return launch_nchw_t<8, 32, 8>(p, st);
+      default: return launch_nchw_t<8, 64, 8>(p, st);
     }
   }
   if (!generic && lx == LAYOUT_NHWC && (d.C % 4) == 0 && ((uintptr_t)p.x % 16) == 0 && ((uintptr_t)p.out % 16) == 0) {
     const int C4 = d.C / 4;
-    if (C4 >= 16) return launch_nhwc_t<16>(p, st);
     if (C4 >= 8) return launch_nhwc_t<8>(p, st);
     if (C4 >= 4) return launch_nhwc_t<4>(p, st);
     if (C4 >= 2) return launch_nhwc_t<2>(p, st);
