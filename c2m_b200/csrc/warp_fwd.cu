@@ -130,113 +130,113 @@ __global__ void __launch_bounds__(TH* TW, (TH * TW <= 256) ? 768 / (TH * TW) : 2
 }
 
 // ---------------------------------------------------------------------------------------------
-// channels-last.  NT threads, tile of TH x TW = NT pixels.  Pass 1: thread t computes the geometry
-// of tile pixel t.  Pass 2: LP consecutive lanes own one pixel at a time and stream its C/4 float4
-// channel groups.
-template <int TH, int TW, int LP, bool HAS_MASK, bool USE_TMA>
-__global__ void __launch_bounds__(TH* TW) fwd_nhwc_kernel(const __grid_constant__ FwdParams p,
-                                                          const __grid_constant__ CUtensorMap tm_flow,
-                                                          const __grid_constant__ CUtensorMap tm_mask) {
-  constexpr int NT = TH * TW;
-  constexpr int GROUPS = NT / LP;  // pixels in flight per pass
-  __shared__ TileSmem<TH, TW> s;
-  __shared__ TileGeo<NT> tg;
+// channels-last.  One CTA = one 8 x 32 pixel tile (non-persistent grid: the block scheduler keeps the
+// SMs full); its flow/mask planes arrive by TMA.  After the one mbarrier wait the eight warps never
+// synchronise with each other again: warp w owns tile row w, every lane computes the geometry of one
+// pixel into the warp's private shared-memory slice, then LP lanes at a time stream a pixel's float4
+// channel groups -- two pixels per lane group in flight, eight 128-bit loads issued before the first use.
+template <int LP, bool HAS_MASK, bool USE_TMA>
+__global__ void __launch_bounds__(256, 6) fwd_nhwc_kernel(const __grid_constant__ FwdParams p,
+                                                       const __grid_constant__ CUtensorMap tm_flow,
+                                                       const __grid_constant__ CUtensorMap tm_mask) {
+  constexpr int TH = 8, TW = 32;
+  constexpr int G = 32 / LP;  // pixels a warp moves side by side
+  __shared__ alignas(128) float s_flow[2][TH][TW];
+  __shared__ alignas(128) float s_mask[TH][TW];
+  __shared__ alignas(8) uint64_t bar;
+  __shared__ int4 s_off[TH][TW];
+  __shared__ float4 s_w[TH][TW];
+  __shared__ float2 s_mk[TH][TW];  // mask value, ok bits
   const Dims& d = p.d;
-  const int tid = threadIdx.x;
-  const int lane_q = tid % LP, grp = tid / LP;
-  const int tx = tid % TW, ty = tid / TW;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tiles_x = (d.W + TW - 1) / TW, tiles_y = (d.H + TH - 1) / TH;
-  const int total = d.N * tiles_y * tiles_x;
+  const int t = blockIdx.x;
+  const int bx = t % tiles_x;
+  const int r = t / tiles_x;
+  const int by = r % tiles_y;
+  const int n = r / tiles_y;
   const int HW = d.H * d.W;
   const int C4 = d.C >> 2;
   const int q0 = blockIdx.y * p.cchunk;  // cchunk counted in float4 groups here
   const int q1 = min(C4, q0 + p.cchunk);
-
-  if (USE_TMA) tile_pipeline_init<TH, TW, HAS_MASK>(s, &tm_flow, &tm_mask, blockIdx.x, total, tiles_x, tiles_y);
-  int buf = 0;
-  uint32_t phases = 0;
-  for (int t = blockIdx.x; t < total; t += gridDim.x) {
-    const int bx = t % tiles_x;
-    const int r = t / tiles_x;
-    const int by = r % tiles_y;
-    const int n = r / tiles_y;
-    {  // pass 1
-      const int i = by * TH + ty, j = bx * TW + tx;
-      const bool live = (i < d.H) & (j < d.W);
-      float fx = 0.f, fy = 0.f, m = 1.f;
-      if (USE_TMA) {
-        const int tn = t + gridDim.x;
-        if (tid == 0 && tn < total) issue_tile<TH, TW, HAS_MASK>(s, &tm_flow, &tm_mask, tn, tiles_x, tiles_y, buf ^ 1);
-        mbar_wait(&s.bar[buf], (phases >> buf) & 1u);
-        phases ^= 1u << buf;
-        fx = s.flow[buf][0][ty][tx];
-        fy = s.flow[buf][1][ty][tx];
-        if (HAS_MASK) m = s.mask[buf][ty][tx];
-        buf ^= 1;
-      } else if (live) {
-        const float* fl = p.flow + (int64_t)n * 2 * HW + i * d.W + j;
-        fx = __ldg(fl);
-        fy = __ldg(fl + HW);
-        if (HAS_MASK) m = __ldg(p.mask + (int64_t)n * HW + i * d.W + j);
-      }
-      Geo g;
-      make_geo<false>(d, fx, fy, min(i, d.H - 1), min(j, d.W - 1), g);
-      store_geo(tg, tid, g, m, d.W, live);
+  const int i = by * TH + warp, j = bx * TW + lane;
+  const bool live = (i < d.H) & (j < d.W);
+  float fx = 0.f, fy = 0.f, m = 1.f;
+  if (USE_TMA) {
+    if (tid == 0) {
+      mbar_init(&bar, 1);
+      mbar_fence_init();
     }
     __syncthreads();
-    const float4* xb = reinterpret_cast<const float4*>(p.x) + (int64_t)(n % d.x_batch) * HW * C4;
-    float4* ob = reinterpret_cast<float4*>(p.out) + (int64_t)n * HW * C4;
-    for (int pp = grp; pp < NT; pp += GROUPS) {
-      const int ok = tg.ok[pp];
-      if (!(ok & 16)) continue;
-      const int4 off = tg.off[pp];
-      const float4 w = tg.w[pp];
-      const float m = tg.m[pp];
-      const int pix = (by * TH + pp / TW) * d.W + bx * TW + pp % TW;
-      const float4* pnw = xb + (int64_t)off.x * C4;
-      const float4* pne = xb + (int64_t)off.y * C4;
-      const float4* psw = xb + (int64_t)off.z * C4;
-      const float4* pse = xb + (int64_t)off.w * C4;
-      float4* po = ob + (int64_t)pix * C4;
-      for (int q = q0 + lane_q; q < q1; q += 2 * LP) {
-        const bool two = (q + LP) < q1;
-        // all corner loads of both channel groups are issued before the first use
-        float4 a0 = ldg_batch(pnw + q), b0 = ldg_batch(pne + q), c0 = ldg_batch(psw + q), e0 = ldg_batch(pse + q);
-        float4 a1 = a0, b1 = b0, c1 = c0, e1 = e0;
-        if (two) {
-          a1 = ldg_batch(pnw + q + LP);
-          b1 = ldg_batch(pne + q + LP);
-          c1 = ldg_batch(psw + q + LP);
-          e1 = ldg_batch(pse + q + LP);
-        }
-        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (!(ok & 1)) a0 = a1 = z;
-        if (!(ok & 2)) b0 = b1 = z;
-        if (!(ok & 4)) c0 = c1 = z;
-        if (!(ok & 8)) e0 = e1 = z;
-#define C2M_BLEND(O, A, B, C, E)                                       \
-  O.x = fmaf(E.x, w.w, fmaf(C.x, w.z, fmaf(B.x, w.y, A.x * w.x)));     \
-  O.y = fmaf(E.y, w.w, fmaf(C.y, w.z, fmaf(B.y, w.y, A.y * w.x)));     \
-  O.z = fmaf(E.z, w.w, fmaf(C.z, w.z, fmaf(B.z, w.y, A.z * w.x)));     \
-  O.w = fmaf(E.w, w.w, fmaf(C.w, w.z, fmaf(B.w, w.y, A.w * w.x)));     \
-  if (HAS_MASK) {                                                      \
-    O.x = __fmul_rn(O.x, m);                                           \
-    O.y = __fmul_rn(O.y, m);                                           \
-    O.z = __fmul_rn(O.z, m);                                           \
-    O.w = __fmul_rn(O.w, m);                                           \
-  }
-        float4 o0, o1;
-        C2M_BLEND(o0, a0, b0, c0, e0)
-        st_stream(po + q, o0);
-        if (two) {
-          C2M_BLEND(o1, a1, b1, c1, e1)
-          st_stream(po + q + LP, o1);
-        }
-#undef C2M_BLEND
-      }
+    if (tid == 0) {
+      constexpr uint32_t bytes = (HAS_MASK ? 3u : 2u) * TH * TW * sizeof(float);
+      mbar_expect_tx(&bar, bytes);
+      tma_load_3d(&s_flow[0][0][0], &tm_flow, &bar, bx * TW, by * TH, n * 2);
+      if (HAS_MASK) tma_load_3d(&s_mask[0][0], &tm_mask, &bar, bx * TW, by * TH, n);
     }
-    __syncthreads();  // geometry of this tile fully consumed before the next pass 1 overwrites it
+    mbar_wait(&bar, 0);
+    fx = s_flow[0][warp][lane];
+    fy = s_flow[1][warp][lane];
+    if (HAS_MASK) m = s_mask[warp][lane];
+  } else if (live) {
+    const float* fl = p.flow + (int64_t)n * 2 * HW + i * d.W + j;
+    fx = __ldg(fl);
+    fy = __ldg(fl + HW);
+    if (HAS_MASK) m = __ldg(p.mask + (int64_t)n * HW + i * d.W + j);
   }
+  if (i >= d.H) return;  // whole warp
+  {
+    Geo g;
+    make_geo<false>(d, fx, fy, i, min(j, d.W - 1), g);
+    s_off[warp][lane] = make_int4(g.y0 * d.W + g.x0, g.y0 * d.W + g.x1, g.y1 * d.W + g.x0, g.y1 * d.W + g.x1);
+    s_w[warp][lane] = make_float4(g.wnw, g.wne, g.wsw, g.wse);
+    const int ok = live ? ((int)g.oknw | ((int)g.okne << 1) | ((int)g.oksw << 2) | ((int)g.okse << 3) | 16) : 0;
+    s_mk[warp][lane] = make_float2(m, __int_as_float(ok));
+  }
+  __syncwarp();
+  const float4* xb = reinterpret_cast<const float4*>(p.x) + (int64_t)(n % d.x_batch) * HW * C4;
+  float4* ob = reinterpret_cast<float4*>(p.out) + ((int64_t)n * HW + (int64_t)i * d.W + bx * TW) * C4;
+  const int lq = lane % LP, grp = lane / LP;
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#define C2M_BLEND(O, A, B, C, E, WT, MK)                                   \
+  O.x = fmaf(E.x, WT.w, fmaf(C.x, WT.z, fmaf(B.x, WT.y, A.x * WT.x)));     \
+  O.y = fmaf(E.y, WT.w, fmaf(C.y, WT.z, fmaf(B.y, WT.y, A.y * WT.x)));     \
+  O.z = fmaf(E.z, WT.w, fmaf(C.z, WT.z, fmaf(B.z, WT.y, A.z * WT.x)));     \
+  O.w = fmaf(E.w, WT.w, fmaf(C.w, WT.z, fmaf(B.w, WT.y, A.w * WT.x)));     \
+  if (HAS_MASK) {                                                          \
+    O.x = __fmul_rn(O.x, MK);                                              \
+    O.y = __fmul_rn(O.y, MK);                                              \
+    O.z = __fmul_rn(O.z, MK);                                              \
+    O.w = __fmul_rn(O.w, MK);                                              \
+  }
+  // One pixel per lane group at a time and few live registers: occupancy (warps per SM), not loads
+  // per thread, is what keeps HBM busy here (tools/microbench/gather_bw.cu).
+  for (int s = 0; s < TW; s += G) {
+    const int pa = s + grp;
+    const float2 mka = s_mk[warp][pa];
+    const int oka = __float_as_int(mka.y);
+    if (!(oka & 16)) continue;  // pixel right of the image edge (no warp-level primitive below)
+    const int4 offa = s_off[warp][pa];
+    const float4 wa = s_w[warp][pa];
+    const float4* pnw = xb + (int64_t)offa.x * C4;
+    const float4* pne = xb + (int64_t)offa.y * C4;
+    const float4* psw = xb + (int64_t)offa.z * C4;
+    const float4* pse = xb + (int64_t)offa.w * C4;
+    float4* po = ob + (int64_t)pa * C4;
+    for (int q = q0 + lq; q < q1; q += LP) {
+      float4 a0 = ldg_batch(pnw + q), b0 = ldg_batch(pne + q), c0 = ldg_batch(psw + q), e0 = ldg_batch(pse + q);
+      if ((oka & 15) != 15) {  // a corner outside the image (zeros padding / exact border hits)
+        if (!(oka & 1)) a0 = z;
+        if (!(oka & 2)) b0 = z;
+        if (!(oka & 4)) c0 = z;
+        if (!(oka & 8)) e0 = z;
+      }
+      float4 o0;
+      C2M_BLEND(o0, a0, b0, c0, e0, wa, mka.x)
+      st_stream(po + q, o0);
+    }
+  }
+#undef C2M_BLEND
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -286,18 +286,13 @@ static int launch_nhwc_t(FwdParams p, cudaStream_t st) {
   const int tiles = d.N * ((d.H + TH - 1) / TH) * ((d.W + TW - 1) / TW);
   const int C4 = d.C / 4;
   int ysplit = 1;
-  const int want = sm_count() * 4;
+  const int want = sm_count() * 8;
   while (tiles * ysplit < want && (C4 / (ysplit * 2)) >= LP) ysplit *= 2;
   p.cchunk = (C4 + ysplit - 1) / ysplit;
   ysplit = (C4 + p.cchunk - 1) / p.cchunk;
   const TileMaps tm = make_tile_maps(d, p.flow, p.mask, TH, TW);
-#define C2M_LAUNCH(MASK, TMA)                                                                  \
-  do {                                                                                            \
-    auto kfn = fwd_nhwc_kernel<TH, TW, LP, MASK, TMA>;                                         \
-    int cap = resident_ctas(reinterpret_cast<const void*>(kfn), TH * TW) / ysplit;             \
-    if (cap < 1) cap = 1;                                                                      \
-    kfn<<<dim3(tiles < cap ? tiles : cap, ysplit), TH * TW, 0, st>>>(p, tm.flow, tm.mask);     \
-  } while (0)
+  const dim3 grid(tiles, ysplit);
+#define C2M_LAUNCH(MASK, TMA) fwd_nhwc_kernel<LP, MASK, TMA><<<grid, TH * TW, 0, st>>>(p, tm.flow, tm.mask)
   if (p.mask) {
     if (tm.ok) C2M_LAUNCH(true, true); else C2M_LAUNCH(true, false);
   } else {
@@ -325,6 +320,7 @@ int launch_fwd(const FwdParams& p, Layout lx, Layout lo, cudaStream_t st) {
   }
   if (!generic && lx == LAYOUT_NHWC && (d.C % 4) == 0 && ((uintptr_t)p.x % 16) == 0 && ((uintptr_t)p.out % 16) == 0) {
     const int C4 = d.C / 4;
+    if (C4 >= 16) return launch_nhwc_t<16>(p, st);
     if (C4 >= 8) return launch_nhwc_t<8>(p, st);
     if (C4 >= 4) return launch_nhwc_t<4>(p, st);
     if (C4 >= 2) return launch_nhwc_t<2>(p, st);
