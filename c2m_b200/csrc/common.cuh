@@ -61,6 +61,7 @@ struct BwdParams {
   int* cnt;                 // [x_batch*H*W] contributions seen per destination pixel
   void* entries;            // [x_batch*H*W][kListCap] ListEntry
   unsigned char* ovf;       // [N*H*W] bit k: corner k of this output pixel did not fit its list
+  int key_mul;              // list entries name their source as pixel index * key_mul
 };
 
 // Per-pixel sampling geometry, shared by forward and backward.
@@ -276,7 +277,7 @@ enum Layout { LAYOUT_NCHW = 0, LAYOUT_NHWC = 1, LAYOUT_OTHER = 2 };
 // Gather-form backward: contributor lists (one per destination pixel of grad-input)
 constexpr int kListCap = 8;  // in-line entries per destination; the tail goes through atomics
 struct ListEntry {
-  int src;    // source (output) pixel index n*H*W + i*W + j
+  int src;    // source (output) pixel n*H*W + i*W + j, times BwdParams::key_mul
   float w;    // bilinear weight * mask
 };
 

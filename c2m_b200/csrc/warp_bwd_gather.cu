@@ -24,11 +24,18 @@
 namespace c2m {
 
 // ---------------------------------------------------------------------------------------------
+// Contributor lists live in the workspace as kListCap/2 planes of int4 -- plane k holds entries 2k and
+// 2k+1 (source pixel, weight, source pixel, weight) of every destination pixel -- so that a warp
+// reading the lists of 32 neighbouring destinations moves whole 512-byte segments.
+__device__ __forceinline__ ListEntry* entry_slot(void* entries, int64_t ndest, int64_t D, int slot) {
+  return reinterpret_cast<ListEntry*>(entries) + (((int64_t)(slot >> 1) * ndest + D) << 1) + (slot & 1);
+}
+
 __global__ void __launch_bounds__(256) bin_kernel(const BwdParams p) {
   const Dims& d = p.d;
   const int HW = d.H * d.W;
   const int64_t total = (int64_t)HW * d.N;
-  ListEntry* entries = reinterpret_cast<ListEntry*>(p.entries);
+  const int64_t ndest = (int64_t)HW * d.x_batch;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
     const int n = (int)(idx / HW);
@@ -40,22 +47,23 @@ __global__ void __launch_bounds__(256) bin_kernel(const BwdParams p) {
     Geo g;
     make_geo<true>(d, fx, fy, i, j, g);
     const int dbase = (n % d.x_batch) * HW;
+    const int D[4] = {dbase + g.y0 * d.W + g.x0, dbase + g.y0 * d.W + g.x1, dbase + g.y1 * d.W + g.x0,
+                      dbase + g.y1 * d.W + g.x1};
+    const float ws[4] = {g.wnw * m, g.wne * m, g.wsw * m, g.wse * m};
+    const bool act[4] = {g.oknw && ws[0] != 0.f, g.okne && ws[1] != 0.f, g.oksw && ws[2] != 0.f,
+                         g.okse && ws[3] != 0.f};
+    int slot[4];
+    // the four slot claims are independent: issue them back to back (one L2 round trip, not four)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) slot[k] = act[k] ? atomicAdd(p.cnt + D[k], 1) : 0;
     unsigned ovf = 0;
-    const int ys[4] = {g.y0, g.y0, g.y1, g.y1};
-    const int xs[4] = {g.x0, g.x1, g.x0, g.x1};
-    const float ws[4] = {g.wnw, g.wne, g.wsw, g.wse};
-    const bool oks[4] = {g.oknw, g.okne, g.oksw, g.okse};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const float w = ws[k] * m;
-      if (oks[k] && w != 0.f) {
-        const int D = dbase + ys[k] * d.W + xs[k];
-        const int slot = atomicAdd(p.cnt + D, 1);
-        if (slot < kListCap) {
-          ListEntry e;
-          e.src = (int)idx;
-          e.w = w;
-          entries[(int64_t)D * kListCap + slot] = e;
+      if (act[k]) {
+        if (slot[k] < kListCap) {
+          // one 8-byte store: (source key, weight)
+          *reinterpret_cast<int2*>(entry_slot(p.entries, ndest, D[k], slot[k])) =
+              make_int2((int)((uint32_t)idx * (uint32_t)p.key_mul), __float_as_int(ws[k]));
         } else {
           ovf |= 1u << k;
         }
@@ -66,204 +74,332 @@ __global__ void __launch_bounds__(256) bin_kernel(const BwdParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// The list tail: output pixels whose contribution did not fit a destination's in-line slots.
+// The list tail: output pixels with a contribution that did not fit a destination's in-line slots.
+// A warp scans 32 flags at a time; each flagged pixel is then handled by the whole warp, lanes
+// across channels (the geometry is recomputed by the owning lane and broadcast).
+__device__ __forceinline__ void red_add_v4(float* p, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+// VEC4: channels-last with C % 4 == 0 and 16-byte aligned tensors -> one 128-bit reduction per four channels
+template <bool VEC4>
 __global__ void __launch_bounds__(256) overflow_kernel(const BwdParams p) {
   const Dims& d = p.d;
   const int HW = d.H * d.W;
   const int64_t total = (int64_t)HW * d.N;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    const unsigned ovf = p.ovf[idx];
-    if (!ovf) continue;
-    const int n = (int)(idx / HW);
-    const int r = (int)(idx - (int64_t)n * HW);
-    const int i = r / d.W, j = r - i * d.W;
-    const float fx = __ldg(p.flow + (int64_t)n * 2 * HW + r);
-    const float fy = __ldg(p.flow + (int64_t)n * 2 * HW + HW + r);
-    const float m = p.mask ? __ldg(p.mask + idx) : 1.f;
-    Geo g;
-    make_geo<true>(d, fx, fy, i, j, g);
-    const int64_t xbase = (int64_t)(n % d.x_batch) * p.xs[0];
-    const int64_t offs[4] = {g.y0 * p.xs[2] + g.x0 * p.xs[3], g.y0 * p.xs[2] + g.x1 * p.xs[3],
-                             g.y1 * p.xs[2] + g.x0 * p.xs[3], g.y1 * p.xs[2] + g.x1 * p.xs[3]};
-    const float ws[4] = {g.wnw * m, g.wne * m, g.wsw * m, g.wse * m};
-    const int64_t gb = (int64_t)n * p.gs[0] + i * p.gs[2] + j * p.gs[3];
-    for (int c = 0; c < d.C; ++c) {
-      const float go = p.gout[gb + c * p.gs[1]];
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (ovf & (1u << k)) atomicAdd(p.gx + xbase + c * p.xs[1] + offs[k], ws[k] * go);
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t base = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32; base < total; base += nwarps * 32) {
+    const int64_t idx = base + lane;
+    const unsigned ovf = idx < total ? p.ovf[idx] : 0u;
+    unsigned any = __ballot_sync(0xffffffffu, ovf != 0u);
+    if (!any) continue;
+    int64_t o0 = 0, o1 = 0, o2 = 0, o3 = 0, gb = 0;
+    float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
+    if (ovf) {
+      const int n = (int)(idx / HW);
+      const int r = (int)(idx - (int64_t)n * HW);
+      const int i = r / d.W, j = r - i * d.W;
+      const float fx = __ldg(p.flow + (int64_t)n * 2 * HW + r);
+      const float fy = __ldg(p.flow + (int64_t)n * 2 * HW + HW + r);
+      const float m = p.mask ? __ldg(p.mask + idx) : 1.f;
+      Geo g;
+      make_geo<true>(d, fx, fy, i, j, g);
+      const int64_t xbase = (int64_t)(n % d.x_batch) * p.xs[0];
+      o0 = xbase + g.y0 * p.xs[2] + g.x0 * p.xs[3];
+      o1 = xbase + g.y0 * p.xs[2] + g.x1 * p.xs[3];
+      o2 = xbase + g.y1 * p.xs[2] + g.x0 * p.xs[3];
+      o3 = xbase + g.y1 * p.xs[2] + g.x1 * p.xs[3];
+      w0 = (ovf & 1u) ? g.wnw * m : 0.f;
+      w1 = (ovf & 2u) ? g.wne * m : 0.f;
+      w2 = (ovf & 4u) ? g.wsw * m : 0.f;
+      w3 = (ovf & 8u) ? g.wse * m : 0.f;
+      gb = (int64_t)n * p.gs[0] + i * p.gs[2] + j * p.gs[3];
+    }
+    while (any) {
+      const int src = __ffs(any) - 1;
+      any &= any - 1;
+      const unsigned f = __shfl_sync(0xffffffffu, ovf, src);
+      const int64_t a0 = __shfl_sync(0xffffffffu, o0, src), a1 = __shfl_sync(0xffffffffu, o1, src);
+      const int64_t a2 = __shfl_sync(0xffffffffu, o2, src), a3 = __shfl_sync(0xffffffffu, o3, src);
+      const float v0 = __shfl_sync(0xffffffffu, w0, src), v1 = __shfl_sync(0xffffffffu, w1, src);
+      const float v2 = __shfl_sync(0xffffffffu, w2, src), v3 = __shfl_sync(0xffffffffu, w3, src);
+      const int64_t g0 = __shfl_sync(0xffffffffu, gb, src);
+      if (VEC4) {
+        for (int c = lane * 4; c < d.C; c += 128) {
+          const float4 go = *reinterpret_cast<const float4*>(p.gout + g0 + c);
+          float* gx = p.gx + c;
+          if (f & 1u) red_add_v4(gx + a0, make_float4(v0 * go.x, v0 * go.y, v0 * go.z, v0 * go.w));
+          if (f & 2u) red_add_v4(gx + a1, make_float4(v1 * go.x, v1 * go.y, v1 * go.z, v1 * go.w));
+          if (f & 4u) red_add_v4(gx + a2, make_float4(v2 * go.x, v2 * go.y, v2 * go.z, v2 * go.w));
+          if (f & 8u) red_add_v4(gx + a3, make_float4(v3 * go.x, v3 * go.y, v3 * go.z, v3 * go.w));
+        }
+      } else {
+        for (int c = lane; c < d.C; c += 32) {
+          const float go = p.gout[g0 + c * p.gs[1]];
+          float* gx = p.gx + c * p.xs[1];
+          if (f & 1u) atomicAdd(gx + a0, v0 * go);
+          if (f & 2u) atomicAdd(gx + a1, v1 * go);
+          if (f & 4u) atomicAdd(gx + a2, v2 * go);
+          if (f & 8u) atomicAdd(gx + a3, v3 * go);
+        }
+      }
     }
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// channels-last gather.  NT = TH*TW threads per tile; LP lanes move one pixel's channels.
-template <int TH, int TW, int LP, bool DO_GX, bool DO_GF, bool HAS_MASK, bool USE_TMA>
-__global__ void __launch_bounds__(TH* TW) gather_nhwc_kernel(const __grid_constant__ BwdParams p,
+// channels-last gather.  One CTA = one 8 x 32 pixel tile, warp w owns tile row w and never waits for
+// another warp after the TMA barrier.  Every pixel of the row plays two roles:
+//   destination  grad-input[pixel] = sum over its contributor list of w * gout[source]
+//   output       grad-flow / grad-mask [pixel] from gout[pixel] and the four corners of x
+// Phase 0: lane t prepares pixel t of the row (geometry, list) into the warp's shared-memory slice;
+//          unused list slots are filled with (own pixel, weight 0) so that phase 1 needs no predicates
+//          for the first four entries.
+// Phase 1: LP lanes at a time stream a pixel's float4 channel groups, NQ groups per lane per pass.
+__device__ __forceinline__ const float4* key_ptr(const char* base, int key) {
+  return reinterpret_cast<const float4*>(base + ((int64_t)(uint32_t)key << 4));  // keys count 16-byte units
+}
+
+template <int LP, int NQ>
+__device__ __forceinline__ void gx_pass(const char* gl, char* po, int cnt, const int4& e0, const int4& e1,
+                                        const int4* ent2, const int4* ent3) {
+  float4 v[4][NQ];
+  const float4* a0 = key_ptr(gl, e0.x);
+  const float4* a1 = key_ptr(gl, e0.z);
+  const float4* a2 = key_ptr(gl, e1.x);
+  const float4* a3 = key_ptr(gl, e1.z);
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    v[0][q] = ldg_batch(a0 + q * LP);
+    v[1][q] = ldg_batch(a1 + q * LP);
+    v[2][q] = ldg_batch(a2 + q * LP);
+    v[3][q] = ldg_batch(a3 + q * LP);
+  }
+  const float w0 = __int_as_float(e0.y), w1 = __int_as_float(e0.w);
+  const float w2 = __int_as_float(e1.y), w3 = __int_as_float(e1.w);
+  float4 acc[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    acc[q].x = fmaf(w3, v[3][q].x, fmaf(w2, v[2][q].x, fmaf(w1, v[1][q].x, w0 * v[0][q].x)));
+    acc[q].y = fmaf(w3, v[3][q].y, fmaf(w2, v[2][q].y, fmaf(w1, v[1][q].y, w0 * v[0][q].y)));
+    acc[q].z = fmaf(w3, v[3][q].z, fmaf(w2, v[2][q].z, fmaf(w1, v[1][q].z, w0 * v[0][q].z)));
+    acc[q].w = fmaf(w3, v[3][q].w, fmaf(w2, v[2][q].w, fmaf(w1, v[1][q].w, w0 * v[0][q].w)));
+  }
+  if (cnt > 4) {  // long list: entries 4..7, two at a time (slots past the count hold weight 0)
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      if (k == 0 || cnt > 6) {
+        const int4 e = k == 0 ? *ent2 : *ent3;
+        const float4* b0 = key_ptr(gl, e.x);
+        const float4* b1 = key_ptr(gl, e.z);
+        float4 u[2][NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          u[0][q] = ldg_batch(b0 + q * LP);
+          u[1][q] = ldg_batch(b1 + q * LP);
+        }
+        const float wa = __int_as_float(e.y), wb = __int_as_float(e.w);
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          acc[q].x = fmaf(wb, u[1][q].x, fmaf(wa, u[0][q].x, acc[q].x));
+          acc[q].y = fmaf(wb, u[1][q].y, fmaf(wa, u[0][q].y, acc[q].y));
+          acc[q].z = fmaf(wb, u[1][q].z, fmaf(wa, u[0][q].z, acc[q].z));
+          acc[q].w = fmaf(wb, u[1][q].w, fmaf(wa, u[0][q].w, acc[q].w));
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) st_stream(reinterpret_cast<float4*>(po) + q * LP, acc[q]);
+}
+
+// sa..se += sum over this lane's channels of gout[c] * x_corner[c]
+template <int LP, int NQ>
+__device__ __forceinline__ void dot_pass(const char* px, const char* pg, const uint4& off, float& sa, float& sb,
+                                         float& sc, float& se) {
+  float4 a[NQ], b[NQ], c[NQ], e[NQ], g[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    a[q] = ldg_batch(reinterpret_cast<const float4*>(px + off.x) + q * LP);
+    b[q] = ldg_batch(reinterpret_cast<const float4*>(px + off.y) + q * LP);
+    c[q] = ldg_batch(reinterpret_cast<const float4*>(px + off.z) + q * LP);
+    e[q] = ldg_batch(reinterpret_cast<const float4*>(px + off.w) + q * LP);
+    g[q] = ldg_batch(reinterpret_cast<const float4*>(pg) + q * LP);
+  }
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    sa = fmaf(g[q].x, a[q].x, fmaf(g[q].y, a[q].y, fmaf(g[q].z, a[q].z, fmaf(g[q].w, a[q].w, sa))));
+    sb = fmaf(g[q].x, b[q].x, fmaf(g[q].y, b[q].y, fmaf(g[q].z, b[q].z, fmaf(g[q].w, b[q].w, sb))));
+    sc = fmaf(g[q].x, c[q].x, fmaf(g[q].y, c[q].y, fmaf(g[q].z, c[q].z, fmaf(g[q].w, c[q].w, sc))));
+    se = fmaf(g[q].x, e[q].x, fmaf(g[q].y, e[q].y, fmaf(g[q].z, e[q].z, fmaf(g[q].w, e[q].w, se))));
+  }
+}
+
+//   LP  lanes per pixel (a warp moves 32/LP pixels side by side)
+//   QI  float4 groups per lane when C/4 == LP*QI exactly, 0 = run-time channel loop
+template <int LP, int QI, bool DO_GX, bool DO_GF, bool HAS_MASK, bool USE_TMA>
+__global__ void __launch_bounds__(256, 3) gather_nhwc_kernel(const __grid_constant__ BwdParams p,
                                                              const __grid_constant__ CUtensorMap tm_flow,
                                                              const __grid_constant__ CUtensorMap tm_mask) {
-  constexpr int NT = TH * TW;
-  constexpr int GROUPS = NT / LP;
-  __shared__ TileSmem<TH, TW> s;
-  __shared__ TileGeo<DO_GF ? NT : 1> tg;
-  __shared__ int s_cnt[DO_GX ? NT : 1];
-  __shared__ int4 s_ent[DO_GX ? NT * (kListCap / 2) : 1];  // this tile's contributor lists
+  constexpr int TH = 8, TW = 32;
+  constexpr int G = 32 / LP;
+  constexpr int NP = kListCap / 2;  // int4 entry pairs per destination
+  static_assert(NP == 4, "phase 1 is written for an eight-entry list");
+  __shared__ alignas(128) float s_flow[DO_GF ? 2 : 1][TH][TW];
+  __shared__ alignas(128) float s_mask[TH][TW];
+  __shared__ alignas(8) uint64_t bar;
+  __shared__ uint4 s_off[DO_GF ? TH : 1][TW];   // byte offsets of the four corners inside the image
+  __shared__ float4 s_w[DO_GF ? TH : 1][TW];    // bilinear weights
+  __shared__ float4 s_aux[DO_GF ? TH : 1][TW];  // ax, ay, gmx, gmy; later the pixel's (gflow_x, gflow_y, gmask)
+  __shared__ float2 s_mk[DO_GF ? TH : 1][TW];   // mask value, in-bounds bits
+  __shared__ int s_cnt[DO_GX ? TH : 1][TW];
+  __shared__ int4 s_ent[DO_GX ? NP : 1][DO_GX ? TH : 1][TW];
   const Dims& d = p.d;
-  const int tid = threadIdx.x;
-  const int lane_q = tid % LP, grp = tid / LP;
-  const int tx = tid % TW, ty = tid / TW;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tiles_x = (d.W + TW - 1) / TW, tiles_y = (d.H + TH - 1) / TH;
-  const int nimg = DO_GF ? d.N : d.x_batch;  // a grad-input-only pass walks the images of x
-  const int total = nimg * tiles_y * tiles_x;
+  const int t = blockIdx.x;
+  const int bx = t % tiles_x;
+  const int r = t / tiles_x;
+  const int by = r % tiles_y;
+  const int n = r / tiles_y;  // DO_GF: frame; gx-only pass: image of x
   const int HW = d.H * d.W;
   const int C4 = d.C >> 2;
-  const ListEntry* entries = reinterpret_cast<const ListEntry*>(p.entries);
-  const float4* g4 = reinterpret_cast<const float4*>(p.gout);
-
-  if (DO_GF && USE_TMA)
-    tile_pipeline_init<TH, TW, HAS_MASK>(s, &tm_flow, &tm_mask, blockIdx.x, total, tiles_x, tiles_y);
-  int buf = 0;
-  uint32_t phases = 0;
-  for (int t = blockIdx.x; t < total; t += gridDim.x) {
-    const int bx = t % tiles_x;
-    const int r = t / tiles_x;
-    const int by = r % tiles_y;
-    const int n = r / tiles_y;
-    if (DO_GX) {  // pass 1a: every thread fetches the contributor list of its own tile pixel
-      const int i = by * TH + ty, j = bx * TW + tx;
-      int c = 0;
-      if ((i < d.H) & (j < d.W)) {
-        const int64_t D = (int64_t)n * HW + i * d.W + j;
-        c = min(__ldg(p.cnt + D), kListCap);
-        const int4* ep = reinterpret_cast<const int4*>(entries + D * kListCap);
-#pragma unroll
-        for (int k = 0; k < kListCap / 2; ++k)
-          if (2 * k < c) s_ent[tid * (kListCap / 2) + k] = __ldg(ep + k);
+  const int i = by * TH + warp, j = bx * TW + lane;
+  const bool live = (i < d.H) & (j < d.W);
+  const int pix = i * d.W + j;
+  float fx = 0.f, fy = 0.f, m = 1.f;
+  if (DO_GF) {
+    if (USE_TMA) {
+      if (tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
       }
-      s_cnt[tid] = c;
-      if (!DO_GF) __syncthreads();
-    }
-    if (DO_GF) {  // pass 1: geometry of this tile's pixels in their output role
-      const int i = by * TH + ty, j = bx * TW + tx;
-      const bool live = (i < d.H) & (j < d.W);
-      float fx = 0.f, fy = 0.f, m = 1.f;
-      if (USE_TMA) {
-        const int tn = t + gridDim.x;
-        if (tid == 0 && tn < total) issue_tile<TH, TW, HAS_MASK>(s, &tm_flow, &tm_mask, tn, tiles_x, tiles_y, buf ^ 1);
-        mbar_wait(&s.bar[buf], (phases >> buf) & 1u);
-        phases ^= 1u << buf;
-        fx = s.flow[buf][0][ty][tx];
-        fy = s.flow[buf][1][ty][tx];
-        if (HAS_MASK) m = s.mask[buf][ty][tx];
-        buf ^= 1;
-      } else if (live) {
-        const float* fl = p.flow + (int64_t)n * 2 * HW + i * d.W + j;
-        fx = __ldg(fl);
-        fy = __ldg(fl + HW);
-        if (HAS_MASK) m = __ldg(p.mask + (int64_t)n * HW + i * d.W + j);
-      }
-      Geo g;
-      make_geo<true>(d, fx, fy, min(i, d.H - 1), min(j, d.W - 1), g);
-      store_geo(tg, tid, g, m, d.W, live);
       __syncthreads();
-    }
-    const float4* xb = reinterpret_cast<const float4*>(p.x) + (int64_t)(n % d.x_batch) * HW * C4;
-    const float4* gfr = g4 + (int64_t)n * HW * C4;  // this frame's gout
-    for (int pp = grp; pp < NT; pp += GROUPS) {
-      const int i = by * TH + pp / TW, j = bx * TW + pp % TW;
-      const bool livepx = (i < d.H) & (j < d.W);  // no `continue`: every lane reaches the shuffles below
-      const int pix = i * d.W + j;
-      if (DO_GX && livepx) {
-        // destination role: this pass owns grad-input pixel (n, i, j) -- valid because with DO_GF
-        // fused the launcher guarantees x_batch == N
-        const int cnt = s_cnt[pp];
-        float4* gxp = reinterpret_cast<float4*>(p.gx) + ((int64_t)n * HW + pix) * C4;
-        for (int q = lane_q; q < C4; q += 2 * LP) {
-          const bool two = (q + LP) < C4;
-          float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
-#pragma unroll
-          for (int kb = 0; kb < kListCap; kb += 4) {
-            if (kb < cnt) {
-              const int4 r0 = s_ent[pp * (kListCap / 2) + (kb >> 1)];
-              const int4 r1 = s_ent[pp * (kListCap / 2) + (kb >> 1) + 1];
-              const int src[4] = {r0.x, r0.z, r1.x, r1.z};
-              const float wk[4] = {__int_as_float(r0.y), __int_as_float(r0.w), __int_as_float(r1.y),
-                                   __int_as_float(r1.w)};
-              float4 v0[4], v1[4];
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                if (kb + k < cnt) {
-                  const float4* sp = g4 + (int64_t)src[k] * C4 + q;
-                  v0[k] = ldg_batch(sp);
-                  if (two) v1[k] = ldg_batch(sp + LP);
-                }
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                if (kb + k < cnt) {
-                  acc0.x = fmaf(wk[k], v0[k].x, acc0.x);
-                  acc0.y = fmaf(wk[k], v0[k].y, acc0.y);
-                  acc0.z = fmaf(wk[k], v0[k].z, acc0.z);
-                  acc0.w = fmaf(wk[k], v0[k].w, acc0.w);
-                  if (two) {
-                    acc1.x = fmaf(wk[k], v1[k].x, acc1.x);
-                    acc1.y = fmaf(wk[k], v1[k].y, acc1.y);
-                    acc1.z = fmaf(wk[k], v1[k].z, acc1.z);
-                    acc1.w = fmaf(wk[k], v1[k].w, acc1.w);
-                  }
-                }
-            }
-          }
-          st_stream(gxp + q, acc0);
-          if (two) st_stream(gxp + q + LP, acc1);
-        }
+      if (tid == 0) {
+        constexpr uint32_t bytes = (HAS_MASK ? 3u : 2u) * TH * TW * sizeof(float);
+        mbar_expect_tx(&bar, bytes);
+        tma_load_3d(&s_flow[0][0][0], &tm_flow, &bar, bx * TW, by * TH, n * 2);
+        if (HAS_MASK) tma_load_3d(&s_mask[0][0], &tm_mask, &bar, bx * TW, by * TH, n);
       }
-      if (DO_GF) {
-        const int ok = tg.ok[pp];
-        const int4 off = tg.off[pp];
-        const float4* pnw = xb + (int64_t)off.x * C4;
-        const float4* pne = xb + (int64_t)off.y * C4;
-        const float4* psw = xb + (int64_t)off.z * C4;
-        const float4* pse = xb + (int64_t)off.w * C4;
-        const float4* gop = gfr + (int64_t)pix * C4;
-        // sa..se = sum_c gout[c] * x_corner[c]: everything else is per-pixel algebra
-        float sa = 0.f, sb = 0.f, sc = 0.f, se = 0.f;
-#pragma unroll 2
-        for (int q = lane_q; livepx && q < C4; q += LP) {
-          const float4 a = ldg_batch(pnw + q), b = ldg_batch(pne + q), c = ldg_batch(psw + q), e2 = ldg_batch(pse + q);
-          const float4 go = ldg_batch(gop + q);
-          sa = fmaf(go.x, a.x, fmaf(go.y, a.y, fmaf(go.z, a.z, fmaf(go.w, a.w, sa))));
-          sb = fmaf(go.x, b.x, fmaf(go.y, b.y, fmaf(go.z, b.z, fmaf(go.w, b.w, sb))));
-          sc = fmaf(go.x, c.x, fmaf(go.y, c.y, fmaf(go.z, c.z, fmaf(go.w, c.w, sc))));
-          se = fmaf(go.x, e2.x, fmaf(go.y, e2.y, fmaf(go.z, e2.z, fmaf(go.w, e2.w, se))));
-        }
-        if (!(ok & 1)) sa = 0.f;  // corners outside the image contribute nothing (ATen within_bounds)
-        if (!(ok & 2)) sb = 0.f;
-        if (!(ok & 4)) sc = 0.f;
-        if (!(ok & 8)) se = 0.f;
-        const float4 w = tg.w[pp];
-        const float4 aux = tg.aux[pp];  // ax, ay, gmx, gmy
-        float gix = (sb - sa) * (1.f - aux.y) + (se - sc) * aux.y;
-        float giy = (sc - sa) * (1.f - aux.x) + (se - sb) * aux.x;
-        float gm = fmaf(se, w.w, fmaf(sc, w.z, fmaf(sb, w.y, sa * w.x)));
+    } else if (live) {
+      const float* fl = p.flow + (int64_t)n * 2 * HW + pix;
+      fx = __ldg(fl);
+      fy = __ldg(fl + HW);
+      if (HAS_MASK) m = __ldg(p.mask + (int64_t)n * HW + pix);
+    }
+  }
+  if (DO_GX && live) {  // this pixel's contributor list (issued before the TMA wait so the two overlap)
+    const int64_t ndest = (int64_t)HW * d.x_batch;
+    const int64_t D = (int64_t)n * HW + pix;
+    const int c = min(__ldg(p.cnt + D), kListCap);
+    const int self = (int)((uint32_t)D * (uint32_t)C4);  // a valid gout pixel for the padding entries
+    const int4* ep = reinterpret_cast<const int4*>(p.entries) + D;
+    int4 e[NP];
 #pragma unroll
-        for (int o = LP >> 1; o > 0; o >>= 1) {
-          gix += __shfl_xor_sync(0xffffffffu, gix, o);
-          giy += __shfl_xor_sync(0xffffffffu, giy, o);
-          gm += __shfl_xor_sync(0xffffffffu, gm, o);
-        }
-        if (lane_q == 0 && livepx) {
-          const float mm = HAS_MASK ? tg.m[pp] : 1.f;  // sums used gout, not gout*mask
-          if (p.gflow) {
-            float* gf = p.gflow + (int64_t)n * 2 * HW + pix;
-            gf[0] = gix * mm * aux.z;
-            gf[HW] = giy * mm * aux.w;
-          }
-          if (p.gmask) p.gmask[(int64_t)n * HW + pix] = gm;
-        }
+    for (int k = 0; k < NP; ++k)
+      if (2 * k < c) e[k] = __ldg(ep + (int64_t)k * ndest);
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+      if (2 * k >= c) { e[k].x = self; e[k].y = 0; }
+      if (2 * k + 1 >= c) { e[k].z = self; e[k].w = 0; }
+      if (k < 2 || 2 * k < c) s_ent[k][warp][lane] = e[k];
+    }
+    s_cnt[warp][lane] = c;
+  }
+  if (DO_GF && USE_TMA) {
+    mbar_wait(&bar, 0);
+    fx = s_flow[0][warp][lane];
+    fy = s_flow[1][warp][lane];
+    if (HAS_MASK) m = s_mask[warp][lane];
+  }
+  if (i >= d.H) return;  // whole warp
+  const uint32_t pxb = (uint32_t)d.C * 4u;  // bytes per pixel
+  if (DO_GF) {
+    Geo g;
+    make_geo<true>(d, fx, fy, i, min(j, d.W - 1), g);
+    s_off[warp][lane] = make_uint4((uint32_t)(g.y0 * d.W + g.x0) * pxb, (uint32_t)(g.y0 * d.W + g.x1) * pxb,
+                                   (uint32_t)(g.y1 * d.W + g.x0) * pxb, (uint32_t)(g.y1 * d.W + g.x1) * pxb);
+    s_w[warp][lane] = make_float4(g.wnw, g.wne, g.wsw, g.wse);
+    s_aux[warp][lane] = make_float4(g.ax, g.ay, g.gmx, g.gmy);
+    const int ok = (int)g.oknw | ((int)g.okne << 1) | ((int)g.oksw << 2) | ((int)g.okse << 3);
+    s_mk[warp][lane] = make_float2(m, __int_as_float(ok));
+  }
+  __syncwarp();
+  const int lq = lane % LP, grp = lane / LP;
+  const int npx = min(TW, d.W - bx * TW);
+  const int nq = QI > 0 ? QI : (C4 - lq + LP - 1) / LP;
+  const char* gl = reinterpret_cast<const char*>(p.gout) + lq * 16;  // + 16 * source key
+  const char* xl = reinterpret_cast<const char*>(p.x) + (int64_t)(n % d.x_batch) * HW * pxb + lq * 16;
+  const int64_t rowpix = (int64_t)n * HW + (int64_t)i * d.W + bx * TW + grp;  // this lane group's first pixel
+  char* gxl = DO_GX ? reinterpret_cast<char*>(p.gx) + rowpix * pxb + lq * 16 : nullptr;
+  const char* gol = reinterpret_cast<const char*>(p.gout) + rowpix * pxb + lq * 16;  // own gout (DO_GF: n is the frame)
+#pragma unroll 1
+  for (int s = 0; s < npx; s += G) {
+    const int pa = s + grp;
+    const bool act = (G == 1) || (pa < npx);
+    if (DO_GX && act) {
+      const int cnt = s_cnt[warp][pa];
+      const int4 e0 = s_ent[0][warp][pa], e1 = s_ent[1][warp][pa];
+      if (QI > 0) {
+        gx_pass<LP, (QI > 0 ? QI : 1)>(gl, gxl, cnt, e0, e1, &s_ent[2][warp][pa], &s_ent[3][warp][pa]);
+      } else {
+#pragma unroll 1
+        for (int qi = 0; qi < nq; ++qi)
+          gx_pass<LP, 1>(gl + qi * (LP * 16), gxl + qi * (LP * 16), cnt, e0, e1, &s_ent[2][warp][pa], &s_ent[3][warp][pa]);
       }
     }
-    __syncthreads();  // tile geometry / lists consumed before the next pass 1
+    if (DO_GF) {
+      // sa..se = sum_c gout[c] * x_corner[c]: everything else is per-pixel algebra
+      float sa = 0.f, sb = 0.f, sc = 0.f, se = 0.f;
+      const int pr = act ? pa : 0;
+      const float2 mk = s_mk[warp][pr];
+      const int ok = __float_as_int(mk.y);
+      if (act) {
+        const uint4 off = s_off[warp][pa];
+        if (QI > 0) {
+          dot_pass<LP, (QI > 0 ? QI : 1)>(xl, gol, off, sa, sb, sc, se);
+        } else {
+#pragma unroll 1
+          for (int qi = 0; qi < nq; ++qi) dot_pass<LP, 1>(xl + qi * (LP * 16), gol + qi * (LP * 16), off, sa, sb, sc, se);
+        }
+      }
+      if (!(ok & 1)) sa = 0.f;  // corners outside the image contribute nothing (ATen within_bounds)
+      if (!(ok & 2)) sb = 0.f;
+      if (!(ok & 4)) sc = 0.f;
+      if (!(ok & 8)) se = 0.f;
+      const float4 w = s_w[warp][pr];
+      const float4 aux = s_aux[warp][pr];  // ax, ay, gmx, gmy
+      float gix = (sb - sa) * (1.f - aux.y) + (se - sc) * aux.y;
+      float giy = (sc - sa) * (1.f - aux.x) + (se - sb) * aux.x;
+      float gm = fmaf(se, w.w, fmaf(sc, w.z, fmaf(sb, w.y, sa * w.x)));
+#pragma unroll
+      for (int o = LP >> 1; o > 0; o >>= 1) {
+        gix += __shfl_xor_sync(0xffffffffu, gix, o);
+        giy += __shfl_xor_sync(0xffffffffu, giy, o);
+        gm += __shfl_xor_sync(0xffffffffu, gm, o);
+      }
+      // (the shuffles above are the convergence point between the group's reads of slot `pa` and this write)
+      if (lq == 0 && act) {
+        const float mm = HAS_MASK ? mk.x : 1.f;  // the sums used gout, not gout*mask
+        s_aux[warp][pa] = make_float4(gix * mm * aux.z, giy * mm * aux.w, gm, 0.f);
+      }
+    }
+    if (DO_GX) gxl += G * pxb;
+    gol += G * pxb;
+  }
+  if (DO_GF) {
+    __syncwarp();
+    if (live) {
+      const float4 res = s_aux[warp][lane];
+      if (p.gflow) {
+        float* gf = p.gflow + (int64_t)n * 2 * HW + pix;
+        gf[0] = res.x;
+        gf[HW] = res.y;
+      }
+      if (p.gmask) p.gmask[(int64_t)n * HW + pix] = res.z;
+    }
   }
 }
 
@@ -283,7 +419,6 @@ __global__ void __launch_bounds__(TH* TW, 2) gather_nchw_kernel(const __grid_con
   const int HW = d.H * d.W;
   const int c0 = blockIdx.y * p.cchunk;
   const int nc = min(p.cchunk, d.C - c0);
-  const ListEntry* entries = reinterpret_cast<const ListEntry*>(p.entries);
 
   if (DO_GF && USE_TMA)
     tile_pipeline_init<TH, TW, HAS_MASK>(s, &tm_flow, &tm_mask, blockIdx.x, total, tiles_x, tiles_y);
@@ -321,12 +456,13 @@ __global__ void __launch_bounds__(TH* TW, 2) gather_nchw_kernel(const __grid_con
       float sw[kListCap];
       if (DO_GX) {
         const int64_t D = (int64_t)n * HW + pix;
+        const int64_t ndest = (int64_t)HW * d.x_batch;
         cnt = min(__ldg(p.cnt + D), kListCap);
-        const int4* ep = reinterpret_cast<const int4*>(entries + D * kListCap);
+        const int4* ep = reinterpret_cast<const int4*>(p.entries) + D;
 #pragma unroll
         for (int k = 0; k < kListCap; k += 2) {
           if (k < cnt) {
-            const int4 raw = __ldg(ep + (k >> 1));
+            const int4 raw = __ldg(ep + (int64_t)(k >> 1) * ndest);
             const int s0 = raw.x, s1 = raw.z;
             if (REPEAT) {
               soff[k] = (int64_t)(s0 / HW) * d.C * HW + (s0 % HW);
@@ -442,6 +578,8 @@ bool gather_supported(const BwdParams& p, Layout lx, Layout lg) {
   if (lx == LAYOUT_NHWC) {
     if ((d.C & 3) || ((uintptr_t)p.x & 15) || ((uintptr_t)p.gout & 15) || (p.gx && ((uintptr_t)p.gx & 15)))
       return false;
+    if ((int64_t)d.H * d.W * d.C >= (1ll << 30)) return false;  // 32-bit byte offsets inside one image
+    if ((int64_t)d.N * d.H * d.W * (d.C / 4) >= (1ll << 32)) return false;  // 32-bit source keys (16-byte units)
   }
   return true;
 }
@@ -452,7 +590,7 @@ static int grid1d(int64_t total) {
   return (int)(blocks > cap ? cap : (blocks < 1 ? 1 : blocks));
 }
 
-template <int LP, bool DO_GX, bool DO_GF>
+template <int LP, int QI, bool DO_GX, bool DO_GF>
 static void launch_gather_nhwc(const BwdParams& p, cudaStream_t st) {
   constexpr int TH = 8, TW = 32;
   const Dims& d = p.d;
@@ -461,12 +599,8 @@ static void launch_gather_nhwc(const BwdParams& p, cudaStream_t st) {
   TileMaps tm;
   memset(&tm, 0, sizeof(tm));
   if (DO_GF) tm = make_tile_maps(d, p.flow, p.mask, TH, TW);
-#define C2M_LAUNCH(MASK, TMA)                                                                              \
-  do {                                                                                                        \
-    auto kfn = gather_nhwc_kernel<TH, TW, LP, DO_GX, DO_GF, MASK, TMA>;                                    \
-    const int cap = resident_ctas(reinterpret_cast<const void*>(kfn), TH * TW);                            \
-    kfn<<<dim3(tiles < cap ? tiles : cap), TH * TW, 0, st>>>(p, tm.flow, tm.mask);                         \
-  } while (0)
+#define C2M_LAUNCH(MASK, TMA) \
+  gather_nhwc_kernel<LP, QI, DO_GX, DO_GF, MASK, TMA><<<tiles, TH * TW, 0, st>>>(p, tm.flow, tm.mask)
   if (p.mask) {
     if (tm.ok) C2M_LAUNCH(true, true); else C2M_LAUNCH(true, false);
   } else {
@@ -479,10 +613,20 @@ static void launch_gather_nhwc(const BwdParams& p, cudaStream_t st) {
 template <bool DO_GX, bool DO_GF>
 static void launch_gather_nhwc_lp(const BwdParams& p, cudaStream_t st) {
   const int C4 = p.d.C / 4;
-  if (C4 >= 8) launch_gather_nhwc<8, DO_GX, DO_GF>(p, st);  // 8 lanes x 2 float4 cover 64 channels per step
-  else if (C4 >= 4) launch_gather_nhwc<4, DO_GX, DO_GF>(p, st);
-  else if (C4 >= 2) launch_gather_nhwc<2, DO_GX, DO_GF>(p, st);
-  else launch_gather_nhwc<1, DO_GX, DO_GF>(p, st);
+  switch (C4) {  // two float4 groups per lane where C allows: half the per-pixel overhead of one
+    case 1: return launch_gather_nhwc<1, 1, DO_GX, DO_GF>(p, st);
+    case 2: return launch_gather_nhwc<1, 2, DO_GX, DO_GF>(p, st);
+    case 4: return launch_gather_nhwc<2, 2, DO_GX, DO_GF>(p, st);
+    case 8: return launch_gather_nhwc<4, 2, DO_GX, DO_GF>(p, st);
+    case 16: return launch_gather_nhwc<8, 2, DO_GX, DO_GF>(p, st);
+    case 32: return launch_gather_nhwc<16, 2, DO_GX, DO_GF>(p, st);
+    case 64: return launch_gather_nhwc<32, 2, DO_GX, DO_GF>(p, st);
+    default: break;
+  }
+  if (C4 >= 24) return launch_gather_nhwc<32, 0, DO_GX, DO_GF>(p, st);
+  if (C4 >= 12) return launch_gather_nhwc<16, 0, DO_GX, DO_GF>(p, st);
+  if (C4 >= 6) return launch_gather_nhwc<8, 0, DO_GX, DO_GF>(p, st);
+  return launch_gather_nhwc<4, 0, DO_GX, DO_GF>(p, st);
 }
 
 template <bool DO_GX, bool DO_GF, bool REPEAT>
@@ -531,6 +675,7 @@ int launch_bwd_gather(const BwdParams& pin, Layout lx, void* workspace, size_t w
     p.cnt = w.cnt;
     p.entries = w.entries;
     p.ovf = w.ovf;
+    p.key_mul = lx == LAYOUT_NHWC ? d.C / 4 : 1;  // channels-last lists address gout in 16-byte units
     if (cudaMemsetAsync(p.cnt, 0, (size_t)d.x_batch * d.H * d.W * sizeof(int), st) != cudaSuccess) return C2M_ERR_CUDA;
     bin_kernel<<<grid1d((int64_t)d.N * d.H * d.W), 256, 0, st>>>(p);
     count_launch();
@@ -555,7 +700,10 @@ int launch_bwd_gather(const BwdParams& pin, Layout lx, void* workspace, size_t w
     }
   }
   if (p.gx) {
-    overflow_kernel<<<grid1d((int64_t)d.N * d.H * d.W), 256, 0, st>>>(p);
+    if (lx == LAYOUT_NHWC)  // gather_supported() has checked C % 4 and the 16-byte alignment
+      overflow_kernel<true><<<grid1d((int64_t)d.N * d.H * d.W), 256, 0, st>>>(p);
+    else
+      overflow_kernel<false><<<grid1d((int64_t)d.N * d.H * d.W), 256, 0, st>>>(p);
     count_launch();
   }
   return C2M_OK;

@@ -133,20 +133,23 @@ __global__ void __launch_bounds__(TH* TW, (TH * TW <= 256) ? 768 / (TH * TW) : 2
 // channels-last.  One CTA = one 8 x 32 pixel tile (non-persistent grid: the block scheduler keeps the
 // SMs full); its flow/mask planes arrive by TMA.  After the one mbarrier wait the eight warps never
 // synchronise with each other again: warp w owns tile row w, every lane computes the geometry of one
-// pixel into the warp's private shared-memory slice, then LP lanes at a time stream a pixel's float4
-// channel groups -- two pixels per lane group in flight, eight 128-bit loads issued before the first use.
-template <int LP, bool HAS_MASK, bool USE_TMA>
+// pixel into the warp's private shared-memory slice (corner positions as 32-bit BYTE offsets into the
+// image, so that an address is one add), then LP lanes at a time stream a pixel's float4 channel
+// groups: four 128-bit corner loads issued back to back, one 128-bit streaming store.
+//   LP  lanes per pixel (a warp moves 32/LP pixels side by side)
+//   QI  float4 groups per lane when C/4 == LP*QI exactly, 0 = run-time channel loop
+template <int LP, int QI, bool HAS_MASK, bool USE_TMA>
 __global__ void __launch_bounds__(256, 6) fwd_nhwc_kernel(const __grid_constant__ FwdParams p,
-                                                       const __grid_constant__ CUtensorMap tm_flow,
-                                                       const __grid_constant__ CUtensorMap tm_mask) {
+                                                          const __grid_constant__ CUtensorMap tm_flow,
+                                                          const __grid_constant__ CUtensorMap tm_mask) {
   constexpr int TH = 8, TW = 32;
   constexpr int G = 32 / LP;  // pixels a warp moves side by side
   __shared__ alignas(128) float s_flow[2][TH][TW];
   __shared__ alignas(128) float s_mask[TH][TW];
   __shared__ alignas(8) uint64_t bar;
-  __shared__ int4 s_off[TH][TW];
-  __shared__ float4 s_w[TH][TW];
-  __shared__ float2 s_mk[TH][TW];  // mask value, ok bits
+  __shared__ uint4 s_off[TH][TW];   // byte offsets of nw, ne, sw, se inside the image
+  __shared__ float4 s_w[TH][TW];    // bilinear weights
+  __shared__ float2 s_mk[TH][TW];   // mask value, in-bounds bits
   const Dims& d = p.d;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tiles_x = (d.W + TW - 1) / TW, tiles_y = (d.H + TH - 1) / TH;
@@ -156,9 +159,6 @@ __global__ void __launch_bounds__(256, 6) fwd_nhwc_kernel(const __grid_constant_
   const int by = r % tiles_y;
   const int n = r / tiles_y;
   const int HW = d.H * d.W;
-  const int C4 = d.C >> 2;
-  const int q0 = blockIdx.y * p.cchunk;  // cchunk counted in float4 groups here
-  const int q1 = min(C4, q0 + p.cchunk);
   const int i = by * TH + warp, j = bx * TW + lane;
   const bool live = (i < d.H) & (j < d.W);
   float fx = 0.f, fy = 0.f, m = 1.f;
@@ -185,58 +185,64 @@ __global__ void __launch_bounds__(256, 6) fwd_nhwc_kernel(const __grid_constant_
     if (HAS_MASK) m = __ldg(p.mask + (int64_t)n * HW + i * d.W + j);
   }
   if (i >= d.H) return;  // whole warp
+  const uint32_t pxb = (uint32_t)d.C * 4u;  // bytes per pixel
   {
     Geo g;
     make_geo<false>(d, fx, fy, i, min(j, d.W - 1), g);
-    s_off[warp][lane] = make_int4(g.y0 * d.W + g.x0, g.y0 * d.W + g.x1, g.y1 * d.W + g.x0, g.y1 * d.W + g.x1);
+    s_off[warp][lane] = make_uint4((uint32_t)(g.y0 * d.W + g.x0) * pxb, (uint32_t)(g.y0 * d.W + g.x1) * pxb,
+                                   (uint32_t)(g.y1 * d.W + g.x0) * pxb, (uint32_t)(g.y1 * d.W + g.x1) * pxb);
     s_w[warp][lane] = make_float4(g.wnw, g.wne, g.wsw, g.wse);
-    const int ok = live ? ((int)g.oknw | ((int)g.okne << 1) | ((int)g.oksw << 2) | ((int)g.okse << 3) | 16) : 0;
+    const int ok = (int)g.oknw | ((int)g.okne << 1) | ((int)g.oksw << 2) | ((int)g.okse << 3);
     s_mk[warp][lane] = make_float2(m, __int_as_float(ok));
   }
   __syncwarp();
-  const float4* xb = reinterpret_cast<const float4*>(p.x) + (int64_t)(n % d.x_batch) * HW * C4;
-  float4* ob = reinterpret_cast<float4*>(p.out) + ((int64_t)n * HW + (int64_t)i * d.W + bx * TW) * C4;
   const int lq = lane % LP, grp = lane / LP;
-  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-#define C2M_BLEND(O, A, B, C, E, WT, MK)                                   \
-  O.x = fmaf(E.x, WT.w, fmaf(C.x, WT.z, fmaf(B.x, WT.y, A.x * WT.x)));     \
-  O.y = fmaf(E.y, WT.w, fmaf(C.y, WT.z, fmaf(B.y, WT.y, A.y * WT.x)));     \
-  O.z = fmaf(E.z, WT.w, fmaf(C.z, WT.z, fmaf(B.z, WT.y, A.z * WT.x)));     \
-  O.w = fmaf(E.w, WT.w, fmaf(C.w, WT.z, fmaf(B.w, WT.y, A.w * WT.x)));     \
-  if (HAS_MASK) {                                                          \
-    O.x = __fmul_rn(O.x, MK);                                              \
-    O.y = __fmul_rn(O.y, MK);                                              \
-    O.z = __fmul_rn(O.z, MK);                                              \
-    O.w = __fmul_rn(O.w, MK);                                              \
-  }
-  // One pixel per lane group at a time and few live registers: occupancy (warps per SM), not loads
-  // per thread, is what keeps HBM busy here (tools/microbench/gather_bw.cu).
-  for (int s = 0; s < TW; s += G) {
+  const int npx = min(TW, d.W - bx * TW);  // live pixels of this row segment (warp-uniform)
+  const char* xl = reinterpret_cast<const char*>(p.x) + (int64_t)(n % d.x_batch) * HW * pxb + lq * 16;
+  char* ol = reinterpret_cast<char*>(p.out) + ((int64_t)n * HW + (int64_t)i * d.W + bx * TW + grp) * pxb + lq * 16;
+  const int C4 = d.C >> 2;
+  const int nq = QI > 0 ? QI : (C4 - lq + LP - 1) / LP;  // float4 groups of this lane
+#pragma unroll 1
+  for (int s = 0; s < npx; s += G) {
     const int pa = s + grp;
-    const float2 mka = s_mk[warp][pa];
-    const int oka = __float_as_int(mka.y);
-    if (!(oka & 16)) continue;  // pixel right of the image edge (no warp-level primitive below)
-    const int4 offa = s_off[warp][pa];
-    const float4 wa = s_w[warp][pa];
-    const float4* pnw = xb + (int64_t)offa.x * C4;
-    const float4* pne = xb + (int64_t)offa.y * C4;
-    const float4* psw = xb + (int64_t)offa.z * C4;
-    const float4* pse = xb + (int64_t)offa.w * C4;
-    float4* po = ob + (int64_t)pa * C4;
-    for (int q = q0 + lq; q < q1; q += LP) {
-      float4 a0 = ldg_batch(pnw + q), b0 = ldg_batch(pne + q), c0 = ldg_batch(psw + q), e0 = ldg_batch(pse + q);
-      if ((oka & 15) != 15) {  // a corner outside the image (zeros padding / exact border hits)
-        if (!(oka & 1)) a0 = z;
-        if (!(oka & 2)) b0 = z;
-        if (!(oka & 4)) c0 = z;
-        if (!(oka & 8)) e0 = z;
+    if (G == 1 || pa < npx) {
+      const uint4 off = s_off[warp][pa];
+      const float4 w = s_w[warp][pa];
+      const float2 mk = s_mk[warp][pa];
+      const int ok = __float_as_int(mk.y);
+      const char* px = xl;
+      char* po = ol;
+#pragma unroll 1
+      for (int qi = 0; qi < (QI > 0 ? QI : nq); ++qi) {
+        float4 a = ldg_batch(reinterpret_cast<const float4*>(px + off.x));
+        float4 b = ldg_batch(reinterpret_cast<const float4*>(px + off.y));
+        float4 c = ldg_batch(reinterpret_cast<const float4*>(px + off.z));
+        float4 e = ldg_batch(reinterpret_cast<const float4*>(px + off.w));
+        if (ok != 15) {  // a corner outside the image (zeros padding / exact border hits)
+          const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (!(ok & 1)) a = z;
+          if (!(ok & 2)) b = z;
+          if (!(ok & 4)) c = z;
+          if (!(ok & 8)) e = z;
+        }
+        float4 o;
+        o.x = fmaf(e.x, w.w, fmaf(c.x, w.z, fmaf(b.x, w.y, a.x * w.x)));
+        o.y = fmaf(e.y, w.w, fmaf(c.y, w.z, fmaf(b.y, w.y, a.y * w.x)));
+        o.z = fmaf(e.z, w.w, fmaf(c.z, w.z, fmaf(b.z, w.y, a.z * w.x)));
+        o.w = fmaf(e.w, w.w, fmaf(c.w, w.z, fmaf(b.w, w.y, a.w * w.x)));
+        if (HAS_MASK) {
+          o.x = __fmul_rn(o.x, mk.x);
+          o.y = __fmul_rn(o.y, mk.x);
+          o.z = __fmul_rn(o.z, mk.x);
+          o.w = __fmul_rn(o.w, mk.x);
+        }
+        st_stream(reinterpret_cast<float4*>(po), o);
+        px += LP * 16;
+        po += LP * 16;
       }
-      float4 o0;
-      C2M_BLEND(o0, a0, b0, c0, e0, wa, mka.x)
-      st_stream(po + q, o0);
     }
+    ol += G * pxb;
   }
-#undef C2M_BLEND
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -279,20 +285,13 @@ static int launch_nchw_t(FwdParams p, cudaStream_t st) {
   return C2M_OK;
 }
 
-template <int LP>
-static int launch_nhwc_t(FwdParams p, cudaStream_t st) {
+template <int LP, int QI>
+static int launch_nhwc_t(const FwdParams& p, cudaStream_t st) {
   constexpr int TH = 8, TW = 32;
   const Dims& d = p.d;
   const int tiles = d.N * ((d.H + TH - 1) / TH) * ((d.W + TW - 1) / TW);
-  const int C4 = d.C / 4;
-  int ysplit = 1;
-  const int want = sm_count() * 8;
-  while (tiles * ysplit < want && (C4 / (ysplit * 2)) >= LP) ysplit *= 2;
-  p.cchunk = (C4 + ysplit - 1) / ysplit;
-  ysplit = (C4 + p.cchunk - 1) / p.cchunk;
   const TileMaps tm = make_tile_maps(d, p.flow, p.mask, TH, TW);
-  const dim3 grid(tiles, ysplit);
-#define C2M_LAUNCH(MASK, TMA) fwd_nhwc_kernel<LP, MASK, TMA><<<grid, TH * TW, 0, st>>>(p, tm.flow, tm.mask)
+#define C2M_LAUNCH(MASK, TMA) fwd_nhwc_kernel<LP, QI, MASK, TMA><<<tiles, TH * TW, 0, st>>>(p, tm.flow, tm.mask)
   if (p.mask) {
     if (tm.ok) C2M_LAUNCH(true, true); else C2M_LAUNCH(true, false);
   } else {
@@ -301,6 +300,26 @@ static int launch_nhwc_t(FwdParams p, cudaStream_t st) {
 #undef C2M_LAUNCH
   count_launch();
   return C2M_OK;
+}
+
+// C/4 float4 groups per pixel -> (lanes per pixel, groups per lane)
+static int launch_nhwc(const FwdParams& p, cudaStream_t st) {
+  const int C4 = p.d.C / 4;
+  switch (C4) {
+    case 1: return launch_nhwc_t<1, 1>(p, st);
+    case 2: return launch_nhwc_t<2, 1>(p, st);
+    case 4: return launch_nhwc_t<4, 1>(p, st);
+    case 8: return launch_nhwc_t<8, 1>(p, st);
+    case 16: return launch_nhwc_t<16, 1>(p, st);
+    case 32: return launch_nhwc_t<16, 2>(p, st);
+    case 64: return launch_nhwc_t<16, 4>(p, st);
+    case 128: return launch_nhwc_t<32, 4>(p, st);
+    default: break;
+  }
+  if (C4 >= 24) return launch_nhwc_t<32, 0>(p, st);
+  if (C4 >= 12) return launch_nhwc_t<16, 0>(p, st);
+  if (C4 >= 6) return launch_nhwc_t<8, 0>(p, st);
+  return launch_nhwc_t<4, 0>(p, st);
 }
 
 int launch_fwd(const FwdParams& p, Layout lx, Layout lo, cudaStream_t st) {
@@ -318,14 +337,10 @@ int launch_fwd(const FwdParams& p, Layout lx, Layout lo, cudaStream_t st) {
       default: return launch_nchw_t<8, 64, 8>(p, st);
     }
   }
-  if (!generic && lx == LAYOUT_NHWC && (d.C % 4) == 0 && ((uintptr_t)p.x % 16) == 0 && ((uintptr_t)p.out % 16) == 0) {
-    const int C4 = d.C / 4;
-    if (C4 >= 16) return launch_nhwc_t<16>(p, st);
-    if (C4 >= 8) return launch_nhwc_t<8>(p, st);
-    if (C4 >= 4) return launch_nhwc_t<4>(p, st);
-    if (C4 >= 2) return launch_nhwc_t<2>(p, st);
-    return launch_nhwc_t<1>(p, st);
-  }
+  // the channels-last kernel addresses corners by 32-bit byte offsets inside one image
+  if (!generic && lx == LAYOUT_NHWC && (d.C % 4) == 0 && ((uintptr_t)p.x % 16) == 0 && ((uintptr_t)p.out % 16) == 0 &&
+      (int64_t)d.H * d.W * d.C < (1ll << 30))
+    return launch_nhwc(p, st);
   const int64_t total = (int64_t)d.N * d.H * d.W;
   int64_t blocks = (total + 255) / 256;
   const int64_t cap = (int64_t)sm_count() * 32;

@@ -346,7 +346,10 @@ def test_full_size_properties(dev, cfg):
     # (3) adjointness: <gout, out(x)> == <gx, x> (the scatter is the transpose of the gather)
     lhs = (gout.double() * out.double()).sum().item()
     rhs = (gx.double() * x.double()).sum().item()
-    assert abs(lhs - rhs) <= 1e-5 * max(abs(lhs), 1.0) + 1e-3
+    # both sides are fp32 results summed in fp64: the rounding error scales with the sum of the
+    # magnitudes of the terms (the signed sum cancels to ~1e-7 of it), not with the sum itself
+    scale = (gx.double().abs() * x.double().abs()).sum().item()
+    assert abs(lhs - rhs) <= 1e-6 * scale
     # (4) checksum of the scatter: sum(gx) == sum_pixels g * (sum of in-bounds weights == 1 for border)
     tot = gx.double().sum().item()
     exp = (gout.double() * mask.double()).sum().item()

@@ -1,0 +1,159 @@
+// Standalone micro-benchmark (development tool, not product): cost of claiming list slots for the
+// gather-form backward -- 4 slot claims per output pixel on counters indexed by destination pixel.
+//   A  global returning atomics (what bin_kernel does)
+//   B  global non-returning reductions (lower bound for any global-atomic scheme)
+//   C  64-bit packed pairs: nw/ne (and sw/se) claimed by one 64-bit atomic when the pair is 8-byte aligned
+//   D  shared-memory window: per-tile counters in shared memory (returning ATOMS), one global atomic per
+//      touched destination to reserve a slot range
+//   E  D without the global reservation (pure shared-memory atomics cost)
+#include <cstdio>
+#include <cstdlib>
+#include <cuda_runtime.h>
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); exit(1);} } while (0)
+
+constexpr int W = 512, H = 256, N = 40;
+constexpr int HW = H * W;
+constexpr long long NPIX = (long long)N * HW;
+
+__device__ __forceinline__ unsigned hash(unsigned x) {
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ float gauss(unsigned s) {  // ~N(0,1): sum of 4 uniforms
+  float a = 0.f;
+  for (int k = 0; k < 4; ++k) { s = hash(s + 0x9e3779b9U * (k + 1)); a += (float)(s >> 8) * (1.0f / 16777216.0f); }
+  return (a - 2.0f) * 1.7320508f;
+}
+// destination pixel indices of the four corners of output pixel (n,i,j)
+__device__ __forceinline__ void dests(int n, int i, int j, float noise, int D[4]) {
+  const unsigned s = (unsigned)(n * HW + i * W + j);
+  const float fx = 8.f * __sinf(6.2831853f * i / 128.f) * __cosf(6.2831853f * j / 256.f) + noise * gauss(s * 2u);
+  const float fy = 8.f * __cosf(6.2831853f * i / 128.f) * __sinf(6.2831853f * j / 256.f) + noise * gauss(s * 2u + 1u);
+  const float ix = fminf(W - 1.f, fmaxf(j + fx, 0.f)), iy = fminf(H - 1.f, fmaxf(i + fy, 0.f));
+  const int x0 = (int)floorf(ix), y0 = (int)floorf(iy);
+  const int x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);
+  const int b = n * HW;
+  D[0] = b + y0 * W + x0; D[1] = b + y0 * W + x1; D[2] = b + y1 * W + x0; D[3] = b + y1 * W + x1;
+}
+
+__global__ void __launch_bounds__(256) kA(int* cnt, int* sink, float noise) {
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < NPIX; idx += (long long)gridDim.x * blockDim.x) {
+    const int n = idx / HW, r = idx % HW, i = r / W, j = r % W;
+    int D[4];
+    dests(n, i, j, noise, D);
+    int s[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s[k] = atomicAdd(cnt + D[k], 1);
+    if (s[0] + s[1] + s[2] + s[3] == -12345) sink[0] = 1;
+  }
+}
+__global__ void __launch_bounds__(256) kB(int* cnt, float noise) {
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < NPIX; idx += (long long)gridDim.x * blockDim.x) {
+    const int n = idx / HW, r = idx % HW, i = r / W, j = r % W;
+    int D[4];
+    dests(n, i, j, noise, D);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) atomicAdd(cnt + D[k], 1);  // result unused -> RED
+  }
+}
+__global__ void __launch_bounds__(256) kC(int* cnt, int* sink, float noise) {
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < NPIX; idx += (long long)gridDim.x * blockDim.x) {
+    const int n = idx / HW, r = idx % HW, i = r / W, j = r % W;
+    int D[4];
+    dests(n, i, j, noise, D);
+    int acc = 0;
+#pragma unroll
+    for (int row = 0; row < 2; ++row) {
+      const int a = D[2 * row], b = D[2 * row + 1];
+      if (b == a + 1 && !(a & 1)) {
+        const unsigned long long old = atomicAdd(reinterpret_cast<unsigned long long*>(cnt + a), 0x100000001ull);
+        acc += (int)old + (int)(old >> 32);
+      } else {
+        acc += atomicAdd(cnt + a, 1);
+        if (b != a) acc += atomicAdd(cnt + b, 1);
+      }
+    }
+    if (acc == -12345) sink[0] = 1;
+  }
+}
+// tile 8x32 outputs, window 24 x 64 destinations around the tile
+template <bool RESERVE>
+__global__ void __launch_bounds__(256) kD(int* cnt, int* sink, float noise) {
+  constexpr int WH = 24, WW = 64;
+  __shared__ int win[WH * WW];
+  __shared__ int base[WH * WW];
+  const int tiles_x = W / 32, tiles_y = H / 8;
+  const int t = blockIdx.x, bx = t % tiles_x, by = (t / tiles_x) % tiles_y, n = t / (tiles_x * tiles_y);
+  const int tid = threadIdx.x;
+  for (int k = tid; k < WH * WW; k += 256) win[k] = 0;
+  __syncthreads();
+  const int i = by * 8 + (tid >> 5), j = bx * 32 + (tid & 31);
+  int D[4];
+  dests(n, i, j, noise, D);
+  const int oy = by * 8 - 8, ox = bx * 32 - 16;
+  int lr[4], wi[4];
+  int acc = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int r = D[k] - n * HW, y = r / W - oy, x = r % W - ox;
+    if (y >= 0 && y < WH && x >= 0 && x < WW) {
+      wi[k] = y * WW + x;
+      lr[k] = atomicAdd(&win[wi[k]], 1);
+    } else {
+      wi[k] = -1;
+      lr[k] = atomicAdd(cnt + D[k], 1);
+    }
+  }
+  __syncthreads();
+  if (RESERVE) {
+    for (int k = tid; k < WH * WW; k += 256) {
+      const int c = win[k];
+      if (c) {
+        const int y = k / WW + oy, x = k % WW + ox;
+        base[k] = atomicAdd(cnt + n * HW + y * W + x, c);
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc += lr[k] + (wi[k] >= 0 ? base[wi[k]] : 0);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc += lr[k];
+  }
+  if (acc == -12345) sink[0] = 1;
+}
+
+template <class F>
+static float timeit(F f, int* cnt) {
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  float best = 1e9f;
+  for (int it = 0; it < 4; ++it) {
+    CK(cudaMemset(cnt, 0, NPIX * sizeof(int)));
+    CK(cudaEventRecord(e0));
+    f();
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (it) best = ms < best ? ms : best;
+  }
+  CK(cudaGetLastError());
+  return best;
+}
+
+int main() {
+  int *cnt, *sink;
+  CK(cudaMalloc(&cnt, NPIX * sizeof(int)));
+  CK(cudaMalloc(&sink, 4));
+  const int grid = 148 * 16, tiles = N * (H / 8) * (W / 32);
+  for (float noise : {0.f, 1.f}) {
+    printf("noise %.0f px: %lld pixels, %lld claims\n", noise, NPIX, 4 * NPIX);
+    printf("  A global returning atomics      %7.3f ms\n", timeit([&] { kA<<<grid, 256>>>(cnt, sink, noise); }, cnt));
+    printf("  A' same, grid = all pixels      %7.3f ms\n", timeit([&] { kA<<<(unsigned)(NPIX / 256), 256>>>(cnt, sink, noise); }, cnt));
+    printf("  B global reductions (no return) %7.3f ms\n", timeit([&] { kB<<<grid, 256>>>(cnt, noise); }, cnt));
+    printf("  C 64-bit packed pairs           %7.3f ms\n", timeit([&] { kC<<<grid, 256>>>(cnt, sink, noise); }, cnt));
+    printf("  D smem window + reservation     %7.3f ms\n", timeit([&] { kD<true><<<tiles, 256>>>(cnt, sink, noise); }, cnt));
+    printf("  E smem window only              %7.3f ms\n", timeit([&] { kD<false><<<tiles, 256>>>(cnt, sink, noise); }, cnt));
+  }
+  return 0;
+}
