@@ -3,6 +3,8 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <climits>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -31,6 +33,14 @@ int sm_count() {
     cached_dev = dev;
   }
   return cached;
+}
+
+int prefetch_tiles(int dflt) {
+  static const int v = [] {
+    const char* e = getenv("C2M_WARP_PREFETCH_TILES");
+    return e && *e ? atoi(e) : INT_MIN;
+  }();
+  return v == INT_MIN ? dflt : v;
 }
 
 int resident_ctas(const void* kernel, int threads) {

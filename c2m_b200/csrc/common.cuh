@@ -38,6 +38,7 @@ struct FwdParams {
   float* out;
   int64_t xs[4], os[4];
   int cchunk;  // channels per blockIdx.y slice
+  int pf_tiles;  // channels-last: L2 prefetch distance in tiles (< 0: off)
 };
 
 struct BwdParams {
@@ -61,7 +62,10 @@ struct BwdParams {
   int* cnt;                 // [x_batch*H*W] contributions seen per destination pixel
   void* entries;            // [x_batch*H*W][kListCap] ListEntry
   unsigned char* ovf;       // [N*H*W] bit k: corner k of this output pixel did not fit its list
+  int* ovf_count;           // number of output pixels with a non-zero `ovf`
+  int* ovf_list;            // their indices, in no particular order
   int key_mul;              // list entries name their source as pixel index * key_mul
+  int pf_tiles;             // channels-last: L2 prefetch distance in tiles (< 0: off)
 };
 
 // Per-pixel sampling geometry, shared by forward and backward.
@@ -187,6 +191,11 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
 }
 
+// Bulk L2 prefetch (TMA engine, no destination): `bytes` is a multiple of 16, `p` 16-byte aligned.
+__device__ __forceinline__ void prefetch_l2(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 // streaming (evict-first) accesses for data touched exactly once
 __device__ __forceinline__ void st_stream(float* p, float v) { __stcs(p, v); }
 __device__ __forceinline__ void st_stream(float4* p, float4 v) { __stcs(p, v); }
@@ -201,6 +210,24 @@ __device__ __forceinline__ float4 ldg_batch(const float4* p) {
   asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];"
                : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
                : "l"(p));
+  return v;
+}
+// Predicated flavour: the load is issued only when `on` is set, otherwise the result is zero (no
+// branch, no memory transaction).
+__device__ __forceinline__ float4 ldg_batch_if(const float4* p, bool on) {
+  float4 v;
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      "setp.ne.s32 q, %5, 0;\n"
+      "mov.f32 %0, 0f00000000;\n"
+      "mov.f32 %1, 0f00000000;\n"
+      "mov.f32 %2, 0f00000000;\n"
+      "mov.f32 %3, 0f00000000;\n"
+      "@q ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];\n"
+      "}\n"
+      : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+      : "l"(p), "r"((int)on));
   return v;
 }
 __device__ __forceinline__ float ldg_batch(const float* p) {
@@ -284,6 +311,9 @@ struct ListEntry {
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 int sm_count();
+// L2 prefetch distance of the channels-last kernels, in tiles (< 0: off); the environment variable
+// C2M_WARP_PREFETCH_TILES overrides the kernel's default (tuning hook)
+int prefetch_tiles(int dflt);
 // Number of CTAs of `kernel` (static shared memory only) that are resident on the whole device at once:
 // the grid size of a persistent launch.
 int resident_ctas(const void* kernel, int threads);

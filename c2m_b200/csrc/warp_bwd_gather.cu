@@ -13,7 +13,7 @@
 //                    channels, so its cost is amortised C times); (b) output role -- grad-flow and
 //                    grad-mask of the same pixel from gout and the four corners of x, reduced over
 //                    channels.  Flow/mask tiles are staged by TMA as in the forward.
-//   overflow_kernel  the (rare) list tail.
+//   overflow_kernel  the list tail (compact list of affected output pixels left by bin_kernel).
 //
 // Algorithmic bytes per pixel: read gout (C) + read x (C) + write gx (C) + flow/mask in, gflow/gmask
 // out.  Extra traffic of this formulation: 4 B counter + 64 B list per destination pixel written and
@@ -31,13 +31,22 @@ __device__ __forceinline__ ListEntry* entry_slot(void* entries, int64_t ndest, i
   return reinterpret_cast<ListEntry*>(entries) + (((int64_t)(slot >> 1) * ndest + D) << 1) + (slot & 1);
 }
 
+constexpr int kBinPixelsPerBlock = 2048;
+
 __global__ void __launch_bounds__(256) bin_kernel(const BwdParams p) {
+  __shared__ int s_list[kBinPixelsPerBlock];  // output pixels of this block with a list overflow
+  __shared__ int s_n, s_base;
   const Dims& d = p.d;
   const int HW = d.H * d.W;
   const int64_t total = (int64_t)HW * d.N;
   const int64_t ndest = (int64_t)HW * d.x_batch;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
+  const int64_t blk0 = (int64_t)blockIdx.x * kBinPixelsPerBlock;
+#pragma unroll 1
+  for (int it = 0; it < kBinPixelsPerBlock / 256; ++it) {
+    const int64_t idx = blk0 + it * 256 + threadIdx.x;
+    if (idx >= total) break;
     const int n = (int)(idx / HW);
     const int r = (int)(idx - (int64_t)n * HW);
     const int i = r / d.W, j = r - i * d.W;
@@ -69,37 +78,54 @@ __global__ void __launch_bounds__(256) bin_kernel(const BwdParams p) {
         }
       }
     }
-    p.ovf[idx] = (unsigned char)ovf;
+    if (ovf) {
+      p.ovf[idx] = (unsigned char)ovf;
+      s_list[atomicAdd(&s_n, 1)] = (int)idx;
+    }
   }
+  __syncthreads();
+  const int nl = s_n;
+  if (nl == 0) return;
+  if (threadIdx.x == 0) s_base = atomicAdd(p.ovf_count, nl);
+  __syncthreads();
+  for (int k = threadIdx.x; k < nl; k += 256) p.ovf_list[s_base + k] = s_list[k];
 }
 
 // ---------------------------------------------------------------------------------------------
-// The list tail: output pixels with a contribution that did not fit a destination's in-line slots.
-// A warp scans 32 flags at a time; each flagged pixel is then handled by the whole warp, lanes
-// across channels (the geometry is recomputed by the owning lane and broadcast).
+// The list tail: contributions that did not fit a destination's in-line slots, applied with atomics
+// after the gather has written grad-input.  bin_kernel left a compact list of the affected output
+// pixels; one warp per listed pixel, lanes across channels (every lane recomputes the geometry).
 __device__ __forceinline__ void red_add_v4(float* p, float4 v) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                : "memory");
 }
 
-// VEC4: channels-last with C % 4 == 0 and 16-byte aligned tensors -> one 128-bit reduction per four channels
+// One block takes 256 listed pixels at a time.  Phase A: thread t recomputes the geometry of record t
+// into shared memory.  Phase B: a group of GS lanes per record moves the channels (VEC4: channels-last
+// with C % 4 == 0 and 16-byte aligned tensors, one 128-bit reduction per four channels and corner).
+struct OvfRec {
+  int64_t a[4];  // element offsets of the four destination pixels in gx
+  int64_t g0;    // element offset of the pixel in gout
+  float v[4];    // weight * mask, 0 for corners that did fit their list
+};
+
 template <bool VEC4>
 __global__ void __launch_bounds__(256) overflow_kernel(const BwdParams p) {
+  constexpr int GS = VEC4 ? 16 : 32;
+  constexpr int NG = 256 / GS;
+  __shared__ OvfRec s_rec[256];
   const Dims& d = p.d;
   const int HW = d.H * d.W;
-  const int64_t total = (int64_t)HW * d.N;
-  const int lane = threadIdx.x & 31;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t base = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32; base < total; base += nwarps * 32) {
-    const int64_t idx = base + lane;
-    const unsigned ovf = idx < total ? p.ovf[idx] : 0u;
-    unsigned any = __ballot_sync(0xffffffffu, ovf != 0u);
-    if (!any) continue;
-    int64_t o0 = 0, o1 = 0, o2 = 0, o3 = 0, gb = 0;
-    float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
-    if (ovf) {
-      const int n = (int)(idx / HW);
-      const int r = (int)(idx - (int64_t)n * HW);
+  const int count = *reinterpret_cast<const volatile int*>(p.ovf_count);
+  const int tid = threadIdx.x;
+  const int gl = tid % GS, grp = tid / GS;
+  for (int base = blockIdx.x * 256; base < count; base += gridDim.x * 256) {
+    const int nrec = min(256, count - base);
+    if (tid < nrec) {
+      const int idx = __ldg(p.ovf_list + base + tid);
+      const unsigned f = p.ovf[idx];
+      const int n = idx / HW;
+      const int r = idx - n * HW;
       const int i = r / d.W, j = r - i * d.W;
       const float fx = __ldg(p.flow + (int64_t)n * 2 * HW + r);
       const float fy = __ldg(p.flow + (int64_t)n * 2 * HW + HW + r);
@@ -107,45 +133,45 @@ __global__ void __launch_bounds__(256) overflow_kernel(const BwdParams p) {
       Geo g;
       make_geo<true>(d, fx, fy, i, j, g);
       const int64_t xbase = (int64_t)(n % d.x_batch) * p.xs[0];
-      o0 = xbase + g.y0 * p.xs[2] + g.x0 * p.xs[3];
-      o1 = xbase + g.y0 * p.xs[2] + g.x1 * p.xs[3];
-      o2 = xbase + g.y1 * p.xs[2] + g.x0 * p.xs[3];
-      o3 = xbase + g.y1 * p.xs[2] + g.x1 * p.xs[3];
-      w0 = (ovf & 1u) ? g.wnw * m : 0.f;
-      w1 = (ovf & 2u) ? g.wne * m : 0.f;
-      w2 = (ovf & 4u) ? g.wsw * m : 0.f;
-      w3 = (ovf & 8u) ? g.wse * m : 0.f;
-      gb = (int64_t)n * p.gs[0] + i * p.gs[2] + j * p.gs[3];
+      OvfRec rec;
+      rec.a[0] = xbase + g.y0 * p.xs[2] + g.x0 * p.xs[3];
+      rec.a[1] = xbase + g.y0 * p.xs[2] + g.x1 * p.xs[3];
+      rec.a[2] = xbase + g.y1 * p.xs[2] + g.x0 * p.xs[3];
+      rec.a[3] = xbase + g.y1 * p.xs[2] + g.x1 * p.xs[3];
+      rec.v[0] = (f & 1u) ? g.wnw * m : 0.f;
+      rec.v[1] = (f & 2u) ? g.wne * m : 0.f;
+      rec.v[2] = (f & 4u) ? g.wsw * m : 0.f;
+      rec.v[3] = (f & 8u) ? g.wse * m : 0.f;
+      rec.g0 = (int64_t)n * p.gs[0] + i * p.gs[2] + j * p.gs[3];
+      s_rec[tid] = rec;
     }
-    while (any) {
-      const int src = __ffs(any) - 1;
-      any &= any - 1;
-      const unsigned f = __shfl_sync(0xffffffffu, ovf, src);
-      const int64_t a0 = __shfl_sync(0xffffffffu, o0, src), a1 = __shfl_sync(0xffffffffu, o1, src);
-      const int64_t a2 = __shfl_sync(0xffffffffu, o2, src), a3 = __shfl_sync(0xffffffffu, o3, src);
-      const float v0 = __shfl_sync(0xffffffffu, w0, src), v1 = __shfl_sync(0xffffffffu, w1, src);
-      const float v2 = __shfl_sync(0xffffffffu, w2, src), v3 = __shfl_sync(0xffffffffu, w3, src);
-      const int64_t g0 = __shfl_sync(0xffffffffu, gb, src);
+    __syncthreads();
+#pragma unroll 2
+    for (int k = grp; k < nrec; k += NG) {
+      const OvfRec& rec = s_rec[k];
       if (VEC4) {
-        for (int c = lane * 4; c < d.C; c += 128) {
-          const float4 go = *reinterpret_cast<const float4*>(p.gout + g0 + c);
+        for (int c = gl * 4; c < d.C; c += GS * 4) {
+          const float4 go = ldg_batch(reinterpret_cast<const float4*>(p.gout + rec.g0 + c));
           float* gx = p.gx + c;
-          if (f & 1u) red_add_v4(gx + a0, make_float4(v0 * go.x, v0 * go.y, v0 * go.z, v0 * go.w));
-          if (f & 2u) red_add_v4(gx + a1, make_float4(v1 * go.x, v1 * go.y, v1 * go.z, v1 * go.w));
-          if (f & 4u) red_add_v4(gx + a2, make_float4(v2 * go.x, v2 * go.y, v2 * go.z, v2 * go.w));
-          if (f & 8u) red_add_v4(gx + a3, make_float4(v3 * go.x, v3 * go.y, v3 * go.z, v3 * go.w));
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float v = rec.v[q];
+            if (v != 0.f) red_add_v4(gx + rec.a[q], make_float4(v * go.x, v * go.y, v * go.z, v * go.w));
+          }
         }
       } else {
-        for (int c = lane; c < d.C; c += 32) {
-          const float go = p.gout[g0 + c * p.gs[1]];
+        for (int c = gl; c < d.C; c += GS) {
+          const float go = p.gout[rec.g0 + c * p.gs[1]];
           float* gx = p.gx + c * p.xs[1];
-          if (f & 1u) atomicAdd(gx + a0, v0 * go);
-          if (f & 2u) atomicAdd(gx + a1, v1 * go);
-          if (f & 4u) atomicAdd(gx + a2, v2 * go);
-          if (f & 8u) atomicAdd(gx + a3, v3 * go);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float v = rec.v[q];
+            if (v != 0.f) atomicAdd(gx + rec.a[q], v * go);
+          }
         }
       }
     }
+    __syncthreads();
   }
 }
 
@@ -170,12 +196,14 @@ __device__ __forceinline__ void gx_pass(const char* gl, char* po, int cnt, const
   const float4* a1 = key_ptr(gl, e0.z);
   const float4* a2 = key_ptr(gl, e1.x);
   const float4* a3 = key_ptr(gl, e1.z);
+  // entries past the count hold weight 0: their loads are predicated off (L1 bandwidth is what
+  // bounds this kernel), the arithmetic below stays unconditional
 #pragma unroll
   for (int q = 0; q < NQ; ++q) {
-    v[0][q] = ldg_batch(a0 + q * LP);
-    v[1][q] = ldg_batch(a1 + q * LP);
-    v[2][q] = ldg_batch(a2 + q * LP);
-    v[3][q] = ldg_batch(a3 + q * LP);
+    v[0][q] = ldg_batch_if(a0 + q * LP, cnt > 0);
+    v[1][q] = ldg_batch_if(a1 + q * LP, cnt > 1);
+    v[2][q] = ldg_batch_if(a2 + q * LP, cnt > 2);
+    v[3][q] = ldg_batch_if(a3 + q * LP, cnt > 3);
   }
   const float w0 = __int_as_float(e0.y), w1 = __int_as_float(e0.w);
   const float w2 = __int_as_float(e1.y), w3 = __int_as_float(e1.w);
@@ -198,7 +226,7 @@ __device__ __forceinline__ void gx_pass(const char* gl, char* po, int cnt, const
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
           u[0][q] = ldg_batch(b0 + q * LP);
-          u[1][q] = ldg_batch(b1 + q * LP);
+          u[1][q] = ldg_batch_if(b1 + q * LP, cnt > 5 + 2 * k);
         }
         const float wa = __int_as_float(e.y), wb = __int_as_float(e.w);
 #pragma unroll
@@ -269,6 +297,20 @@ __global__ void __launch_bounds__(256, 3) gather_nhwc_kernel(const __grid_consta
   const int i = by * TH + warp, j = bx * TW + lane;
   const bool live = (i < d.H) & (j < d.W);
   const int pix = i * d.W + j;
+  if (p.pf_tiles >= 0 && lane == 0) {
+    // pull the gout (and x) rows under a tile `pf_tiles` ahead into L2: that tile's gathers land in
+    // this region shifted by the flow
+    const int tp = t + p.pf_tiles;
+    const int pbx = tp % tiles_x, pr = tp / tiles_x, pby = pr % tiles_y, pn = pr / tiles_y;
+    const int pi = pby * TH + warp;
+    if (pn < (DO_GF ? d.N : d.x_batch) && pi < d.H) {
+      const uint32_t cb = (uint32_t)d.C * 4u;
+      const int64_t px0 = (int64_t)pi * d.W + pbx * TW;
+      const uint32_t bytes = (uint32_t)min(TW, d.W - pbx * TW) * cb;
+      prefetch_l2(reinterpret_cast<const char*>(p.gout) + ((int64_t)pn * HW + px0) * cb, bytes);
+      if (DO_GF) prefetch_l2(reinterpret_cast<const char*>(p.x) + ((int64_t)(pn % d.x_batch) * HW + px0) * cb, bytes);
+    }
+  }
   float fx = 0.f, fy = 0.f, m = 1.f;
   if (DO_GF) {
     if (USE_TMA) {
@@ -542,9 +584,12 @@ __global__ void __launch_bounds__(TH* TW, 2) gather_nchw_kernel(const __grid_con
 // host side
 // ---------------------------------------------------------------------------------------------
 struct GatherWs {
-  int* cnt;
+  int* cnt;        // [x_batch*H*W] + the overflow-list length right behind it (one memset clears both)
+  int* ovf_count;
   void* entries;
   unsigned char* ovf;
+  int* ovf_list;
+  size_t cnt_bytes;
   size_t bytes;
 };
 
@@ -555,11 +600,15 @@ static GatherWs carve(void* base, int64_t N, int H, int W, int64_t x_batch) {
   char* b = reinterpret_cast<char*>(base);
   size_t o = 0;
   w.cnt = reinterpret_cast<int*>(b + o);
-  o += up(npix_d * sizeof(int));
+  w.ovf_count = w.cnt + npix_d;
+  w.cnt_bytes = (npix_d + 1) * sizeof(int);
+  o += up(w.cnt_bytes);
   w.entries = b + o;
   o += up(npix_d * kListCap * sizeof(ListEntry));
   w.ovf = reinterpret_cast<unsigned char*>(b + o);
   o += up(npix_o);
+  w.ovf_list = reinterpret_cast<int*>(b + o);
+  o += up(npix_o * sizeof(int));
   w.bytes = o;
   return w;
 }
@@ -584,14 +633,9 @@ bool gather_supported(const BwdParams& p, Layout lx, Layout lg) {
   return true;
 }
 
-static int grid1d(int64_t total) {
-  int64_t blocks = (total + 255) / 256;
-  const int64_t cap = (int64_t)sm_count() * 16;
-  return (int)(blocks > cap ? cap : (blocks < 1 ? 1 : blocks));
-}
-
 template <int LP, int QI, bool DO_GX, bool DO_GF>
-static void launch_gather_nhwc(const BwdParams& p, cudaStream_t st) {
+static void launch_gather_nhwc(BwdParams p, cudaStream_t st) {
+  p.pf_tiles = prefetch_tiles(0);  // measured: own tile, issued at CTA start, is the best distance
   constexpr int TH = 8, TW = 32;
   const Dims& d = p.d;
   const int nimg = DO_GF ? d.N : d.x_batch;
@@ -675,9 +719,12 @@ int launch_bwd_gather(const BwdParams& pin, Layout lx, void* workspace, size_t w
     p.cnt = w.cnt;
     p.entries = w.entries;
     p.ovf = w.ovf;
+    p.ovf_count = w.ovf_count;
+    p.ovf_list = w.ovf_list;
     p.key_mul = lx == LAYOUT_NHWC ? d.C / 4 : 1;  // channels-last lists address gout in 16-byte units
-    if (cudaMemsetAsync(p.cnt, 0, (size_t)d.x_batch * d.H * d.W * sizeof(int), st) != cudaSuccess) return C2M_ERR_CUDA;
-    bin_kernel<<<grid1d((int64_t)d.N * d.H * d.W), 256, 0, st>>>(p);
+    if (cudaMemsetAsync(p.cnt, 0, w.cnt_bytes, st) != cudaSuccess) return C2M_ERR_CUDA;
+    const int64_t total = (int64_t)d.N * d.H * d.W;
+    bin_kernel<<<(unsigned)((total + kBinPixelsPerBlock - 1) / kBinPixelsPerBlock), 256, 0, st>>>(p);
     count_launch();
   }
   const bool fuse = p.gx && need_gf && !repeat;
@@ -700,10 +747,11 @@ int launch_bwd_gather(const BwdParams& pin, Layout lx, void* workspace, size_t w
     }
   }
   if (p.gx) {
+    const int grid = sm_count() * 8;
     if (lx == LAYOUT_NHWC)  // gather_supported() has checked C % 4 and the 16-byte alignment
-      overflow_kernel<true><<<grid1d((int64_t)d.N * d.H * d.W), 256, 0, st>>>(p);
+      overflow_kernel<true><<<grid, 256, 0, st>>>(p);
     else
-      overflow_kernel<false><<<grid1d((int64_t)d.N * d.H * d.W), 256, 0, st>>>(p);
+      overflow_kernel<false><<<grid, 256, 0, st>>>(p);
     count_launch();
   }
   return C2M_OK;

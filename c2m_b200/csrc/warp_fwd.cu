@@ -161,6 +161,18 @@ __global__ void __launch_bounds__(256, 6) fwd_nhwc_kernel(const __grid_constant_
   const int HW = d.H * d.W;
   const int i = by * TH + warp, j = bx * TW + lane;
   const bool live = (i < d.H) & (j < d.W);
+  if (p.pf_tiles >= 0 && lane == 0) {
+    // pull the x rows that lie under a tile `pf_tiles` ahead into L2 (its footprint is that region
+    // shifted by the flow): by the time that tile runs, its gathers are L2 hits
+    const int tp = t + p.pf_tiles;
+    const int pbx = tp % tiles_x, pr = tp / tiles_x, pby = pr % tiles_y, pn = pr / tiles_y;
+    const int pi = pby * TH + warp;
+    if (pn < d.N && pi < d.H) {
+      const uint32_t cb = (uint32_t)d.C * 4u;
+      prefetch_l2(reinterpret_cast<const char*>(p.x) + ((int64_t)(pn % d.x_batch) * HW + (int64_t)pi * d.W + pbx * TW) * cb,
+                  (uint32_t)min(TW, d.W - pbx * TW) * cb);
+    }
+  }
   float fx = 0.f, fy = 0.f, m = 1.f;
   if (USE_TMA) {
     if (tid == 0) {
@@ -286,7 +298,8 @@ static int launch_nchw_t(FwdParams p, cudaStream_t st) {
 }
 
 template <int LP, int QI>
-static int launch_nhwc_t(const FwdParams& p, cudaStream_t st) {
+static int launch_nhwc_t(FwdParams p, cudaStream_t st) {
+  p.pf_tiles = prefetch_tiles(-1);  // measured: the forward gains nothing from it
   constexpr int TH = 8, TW = 32;
   const Dims& d = p.d;
   const int tiles = d.N * ((d.H + TH - 1) / TH) * ((d.W + TW - 1) / TW);
