@@ -64,6 +64,9 @@ struct BwdParams {
   unsigned char* ovf;       // [N*H*W] bit k: corner k of this output pixel did not fit its list
   int* ovf_count;           // number of output pixels with a non-zero `ovf`
   int* ovf_list;            // their indices, in no particular order
+  int n0, nframes;          // the frames [n0, n0 + nframes) a launch covers
+  int lookahead;            // fused binning: a gather CTA of frame n also bins its tile of frame n + lookahead
+  int* done;                // [N] tiles of frame n whose binning has completed (fused binning)
   int key_mul;              // list entries name their source as pixel index * key_mul
   int pf_tiles;             // channels-last: L2 prefetch distance in tiles (< 0: off)
 };

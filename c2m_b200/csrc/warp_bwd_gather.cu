@@ -19,6 +19,8 @@
 // out.  Extra traffic of this formulation: 4 B counter + 64 B list per destination pixel written and
 // read once, 1 B flag per output pixel -- about 1/6 of a C=64 pixel's bytes -- and no zero-fill,
 // no read-modify-write of grad-input.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace c2m {
@@ -31,6 +33,42 @@ __device__ __forceinline__ ListEntry* entry_slot(void* entries, int64_t ndest, i
   return reinterpret_cast<ListEntry*>(entries) + (((int64_t)(slot >> 1) * ndest + D) << 1) + (slot & 1);
 }
 
+// Appends output pixel `idx` = (n, i, j) to the lists of its up-to-four destination pixels.  Returns
+// the corners whose destination list was full (bit k), also recorded in p.ovf[idx].
+__device__ __forceinline__ unsigned bin_pixel(const BwdParams& p, int64_t idx, int n, int i, int j, float fx, float fy,
+                                              float m) {
+  const Dims& d = p.d;
+  const int HW = d.H * d.W;
+  const int64_t ndest = (int64_t)HW * d.x_batch;
+  Geo g;
+  make_geo<true>(d, fx, fy, i, j, g);
+  const int dbase = (n % d.x_batch) * HW;
+  const int D[4] = {dbase + g.y0 * d.W + g.x0, dbase + g.y0 * d.W + g.x1, dbase + g.y1 * d.W + g.x0,
+                    dbase + g.y1 * d.W + g.x1};
+  const float ws[4] = {g.wnw * m, g.wne * m, g.wsw * m, g.wse * m};
+  const bool act[4] = {g.oknw && ws[0] != 0.f, g.okne && ws[1] != 0.f, g.oksw && ws[2] != 0.f,
+                       g.okse && ws[3] != 0.f};
+  int slot[4];
+  // the four slot claims are independent: issue them back to back (one L2 round trip, not four)
+#pragma unroll
+  for (int k = 0; k < 4; ++k) slot[k] = act[k] ? atomicAdd(p.cnt + D[k], 1) : 0;
+  unsigned ovf = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (act[k]) {
+      if (slot[k] < kListCap) {
+        // one 8-byte store: (source key, weight)
+        *reinterpret_cast<int2*>(entry_slot(p.entries, ndest, D[k], slot[k])) =
+            make_int2((int)((uint32_t)idx * (uint32_t)p.key_mul), __float_as_int(ws[k]));
+      } else {
+        ovf |= 1u << k;
+      }
+    }
+  }
+  if (ovf) p.ovf[idx] = (unsigned char)ovf;
+  return ovf;
+}
+
 constexpr int kBinPixelsPerBlock = 2048;
 
 __global__ void __launch_bounds__(256) bin_kernel(const BwdParams p) {
@@ -38,11 +76,10 @@ __global__ void __launch_bounds__(256) bin_kernel(const BwdParams p) {
   __shared__ int s_n, s_base;
   const Dims& d = p.d;
   const int HW = d.H * d.W;
-  const int64_t total = (int64_t)HW * d.N;
-  const int64_t ndest = (int64_t)HW * d.x_batch;
+  const int64_t total = (int64_t)HW * (p.n0 + p.nframes);
   if (threadIdx.x == 0) s_n = 0;
   __syncthreads();
-  const int64_t blk0 = (int64_t)blockIdx.x * kBinPixelsPerBlock;
+  const int64_t blk0 = (int64_t)HW * p.n0 + (int64_t)blockIdx.x * kBinPixelsPerBlock;
 #pragma unroll 1
   for (int it = 0; it < kBinPixelsPerBlock / 256; ++it) {
     const int64_t idx = blk0 + it * 256 + threadIdx.x;
@@ -53,35 +90,7 @@ __global__ void __launch_bounds__(256) bin_kernel(const BwdParams p) {
     const float fx = __ldg(p.flow + (int64_t)n * 2 * HW + r);
     const float fy = __ldg(p.flow + (int64_t)n * 2 * HW + HW + r);
     const float m = p.mask ? __ldg(p.mask + idx) : 1.f;
-    Geo g;
-    make_geo<true>(d, fx, fy, i, j, g);
-    const int dbase = (n % d.x_batch) * HW;
-    const int D[4] = {dbase + g.y0 * d.W + g.x0, dbase + g.y0 * d.W + g.x1, dbase + g.y1 * d.W + g.x0,
-                      dbase + g.y1 * d.W + g.x1};
-    const float ws[4] = {g.wnw * m, g.wne * m, g.wsw * m, g.wse * m};
-    const bool act[4] = {g.oknw && ws[0] != 0.f, g.okne && ws[1] != 0.f, g.oksw && ws[2] != 0.f,
-                         g.okse && ws[3] != 0.f};
-    int slot[4];
-    // the four slot claims are independent: issue them back to back (one L2 round trip, not four)
-#pragma unroll
-    for (int k = 0; k < 4; ++k) slot[k] = act[k] ? atomicAdd(p.cnt + D[k], 1) : 0;
-    unsigned ovf = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (act[k]) {
-        if (slot[k] < kListCap) {
-          // one 8-byte store: (source key, weight)
-          *reinterpret_cast<int2*>(entry_slot(p.entries, ndest, D[k], slot[k])) =
-              make_int2((int)((uint32_t)idx * (uint32_t)p.key_mul), __float_as_int(ws[k]));
-        } else {
-          ovf |= 1u << k;
-        }
-      }
-    }
-    if (ovf) {
-      p.ovf[idx] = (unsigned char)ovf;
-      s_list[atomicAdd(&s_n, 1)] = (int)idx;
-    }
+    if (bin_pixel(p, idx, n, i, j, fx, fy, m)) s_list[atomicAdd(&s_n, 1)] = (int)idx;
   }
   __syncthreads();
   const int nl = s_n;
@@ -188,16 +197,16 @@ __device__ __forceinline__ const float4* key_ptr(const char* base, int key) {
   return reinterpret_cast<const float4*>(base + ((int64_t)(uint32_t)key << 4));  // keys count 16-byte units
 }
 
+// The destination role and the output role of a step are each split into "issue the loads" and "use
+// them", so that the fused kernel can put both roles' loads in flight before it waits for either.
 template <int LP, int NQ>
-__device__ __forceinline__ void gx_pass(const char* gl, char* po, int cnt, const int4& e0, const int4& e1,
-                                        const int4* ent2, const int4* ent3) {
-  float4 v[4][NQ];
+__device__ __forceinline__ void gx_issue(const char* gl, int cnt, const int4& e0, const int4& e1, float4 (&v)[4][NQ]) {
   const float4* a0 = key_ptr(gl, e0.x);
   const float4* a1 = key_ptr(gl, e0.z);
   const float4* a2 = key_ptr(gl, e1.x);
   const float4* a3 = key_ptr(gl, e1.z);
   // entries past the count hold weight 0: their loads are predicated off (L1 bandwidth is what
-  // bounds this kernel), the arithmetic below stays unconditional
+  // bounds this kernel), the arithmetic stays unconditional
 #pragma unroll
   for (int q = 0; q < NQ; ++q) {
     v[0][q] = ldg_batch_if(a0 + q * LP, cnt > 0);
@@ -205,6 +214,11 @@ __device__ __forceinline__ void gx_pass(const char* gl, char* po, int cnt, const
     v[2][q] = ldg_batch_if(a2 + q * LP, cnt > 2);
     v[3][q] = ldg_batch_if(a3 + q * LP, cnt > 3);
   }
+}
+
+template <int LP, int NQ>
+__device__ __forceinline__ void gx_finish(const char* gl, char* po, int cnt, const int4& e0, const int4& e1,
+                                          const int4* ent2, const int4* ent3, const float4 (&v)[4][NQ]) {
   const float w0 = __int_as_float(e0.y), w1 = __int_as_float(e0.w);
   const float w2 = __int_as_float(e1.y), w3 = __int_as_float(e1.w);
   float4 acc[NQ];
@@ -243,31 +257,43 @@ __device__ __forceinline__ void gx_pass(const char* gl, char* po, int cnt, const
   for (int q = 0; q < NQ; ++q) st_stream(reinterpret_cast<float4*>(po) + q * LP, acc[q]);
 }
 
-// sa..se += sum over this lane's channels of gout[c] * x_corner[c]
-template <int LP, int NQ>
-__device__ __forceinline__ void dot_pass(const char* px, const char* pg, const uint4& off, float& sa, float& sb,
-                                         float& sc, float& se) {
+template <int NQ>
+struct DotRegs {
   float4 a[NQ], b[NQ], c[NQ], e[NQ], g[NQ];
+};
+
+template <int LP, int NQ>
+__device__ __forceinline__ void dot_issue(const char* px, const char* pg, const uint4& off, DotRegs<NQ>& r) {
 #pragma unroll
   for (int q = 0; q < NQ; ++q) {
-    a[q] = ldg_batch(reinterpret_cast<const float4*>(px + off.x) + q * LP);
-    b[q] = ldg_batch(reinterpret_cast<const float4*>(px + off.y) + q * LP);
-    c[q] = ldg_batch(reinterpret_cast<const float4*>(px + off.z) + q * LP);
-    e[q] = ldg_batch(reinterpret_cast<const float4*>(px + off.w) + q * LP);
-    g[q] = ldg_batch(reinterpret_cast<const float4*>(pg) + q * LP);
+    r.a[q] = ldg_batch(reinterpret_cast<const float4*>(px + off.x) + q * LP);
+    r.b[q] = ldg_batch(reinterpret_cast<const float4*>(px + off.y) + q * LP);
+    r.c[q] = ldg_batch(reinterpret_cast<const float4*>(px + off.z) + q * LP);
+    r.e[q] = ldg_batch(reinterpret_cast<const float4*>(px + off.w) + q * LP);
+    r.g[q] = ldg_batch(reinterpret_cast<const float4*>(pg) + q * LP);
   }
+}
+
+// sa..se += sum over this lane's channels of gout[c] * x_corner[c]
+template <int NQ>
+__device__ __forceinline__ void dot_finish(const DotRegs<NQ>& r, float& sa, float& sb, float& sc, float& se) {
 #pragma unroll
   for (int q = 0; q < NQ; ++q) {
-    sa = fmaf(g[q].x, a[q].x, fmaf(g[q].y, a[q].y, fmaf(g[q].z, a[q].z, fmaf(g[q].w, a[q].w, sa))));
-    sb = fmaf(g[q].x, b[q].x, fmaf(g[q].y, b[q].y, fmaf(g[q].z, b[q].z, fmaf(g[q].w, b[q].w, sb))));
-    sc = fmaf(g[q].x, c[q].x, fmaf(g[q].y, c[q].y, fmaf(g[q].z, c[q].z, fmaf(g[q].w, c[q].w, sc))));
-    se = fmaf(g[q].x, e[q].x, fmaf(g[q].y, e[q].y, fmaf(g[q].z, e[q].z, fmaf(g[q].w, e[q].w, se))));
+    sa = fmaf(r.g[q].x, r.a[q].x, fmaf(r.g[q].y, r.a[q].y, fmaf(r.g[q].z, r.a[q].z, fmaf(r.g[q].w, r.a[q].w, sa))));
+    sb = fmaf(r.g[q].x, r.b[q].x, fmaf(r.g[q].y, r.b[q].y, fmaf(r.g[q].z, r.b[q].z, fmaf(r.g[q].w, r.b[q].w, sb))));
+    sc = fmaf(r.g[q].x, r.c[q].x, fmaf(r.g[q].y, r.c[q].y, fmaf(r.g[q].z, r.c[q].z, fmaf(r.g[q].w, r.c[q].w, sc))));
+    se = fmaf(r.g[q].x, r.e[q].x, fmaf(r.g[q].y, r.e[q].y, fmaf(r.g[q].z, r.e[q].z, fmaf(r.g[q].w, r.e[q].w, se))));
   }
 }
 
 //   LP  lanes per pixel (a warp moves 32/LP pixels side by side)
 //   QI  float4 groups per lane when C/4 == LP*QI exactly, 0 = run-time channel loop
-template <int LP, int QI, bool DO_GX, bool DO_GF, bool HAS_MASK, bool USE_TMA>
+//   DO_BIN  fused binning: the CTA of (frame n, tile t) first bins tile t of frame n + lookahead (the slot
+//           claims and list stores then overlap the bandwidth-bound streaming of other CTAs instead of
+//           occupying a launch of their own); a frame's lists are read only once every tile of it has
+//           been binned, which -- CTAs being dispatched in index order -- earlier CTAs of this launch
+//           (or the preceding bin_kernel launch) have long done.
+template <int LP, int QI, bool DO_GX, bool DO_GF, bool HAS_MASK, bool USE_TMA, bool DO_BIN>
 __global__ void __launch_bounds__(256, 3) gather_nhwc_kernel(const __grid_constant__ BwdParams p,
                                                              const __grid_constant__ CUtensorMap tm_flow,
                                                              const __grid_constant__ CUtensorMap tm_mask) {
@@ -284,6 +310,8 @@ __global__ void __launch_bounds__(256, 3) gather_nhwc_kernel(const __grid_consta
   __shared__ float2 s_mk[DO_GF ? TH : 1][TW];   // mask value, in-bounds bits
   __shared__ int s_cnt[DO_GX ? TH : 1][TW];
   __shared__ int4 s_ent[DO_GX ? NP : 1][DO_GX ? TH : 1][TW];
+  __shared__ int s_olist[DO_BIN ? TH * TW : 1];  // pixels binned by this CTA whose list overflowed
+  __shared__ int s_on, s_obase;
   const Dims& d = p.d;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tiles_x = (d.W + TW - 1) / TW, tiles_y = (d.H + TH - 1) / TH;
@@ -291,7 +319,7 @@ __global__ void __launch_bounds__(256, 3) gather_nhwc_kernel(const __grid_consta
   const int bx = t % tiles_x;
   const int r = t / tiles_x;
   const int by = r % tiles_y;
-  const int n = r / tiles_y;  // DO_GF: frame; gx-only pass: image of x
+  const int n = p.n0 + r / tiles_y;  // DO_GF: frame; gx-only pass: image of x
   const int HW = d.H * d.W;
   const int C4 = d.C >> 2;
   const int i = by * TH + warp, j = bx * TW + lane;
@@ -301,9 +329,9 @@ __global__ void __launch_bounds__(256, 3) gather_nhwc_kernel(const __grid_consta
     // pull the gout (and x) rows under a tile `pf_tiles` ahead into L2: that tile's gathers land in
     // this region shifted by the flow
     const int tp = t + p.pf_tiles;
-    const int pbx = tp % tiles_x, pr = tp / tiles_x, pby = pr % tiles_y, pn = pr / tiles_y;
+    const int pbx = tp % tiles_x, pr = tp / tiles_x, pby = pr % tiles_y, pn = p.n0 + pr / tiles_y;
     const int pi = pby * TH + warp;
-    if (pn < (DO_GF ? d.N : d.x_batch) && pi < d.H) {
+    if (pn < p.n0 + p.nframes && pi < d.H) {
       const uint32_t cb = (uint32_t)d.C * 4u;
       const int64_t px0 = (int64_t)pi * d.W + pbx * TW;
       const uint32_t bytes = (uint32_t)min(TW, d.W - pbx * TW) * cb;
@@ -332,16 +360,53 @@ __global__ void __launch_bounds__(256, 3) gather_nhwc_kernel(const __grid_consta
       if (HAS_MASK) m = __ldg(p.mask + (int64_t)n * HW + pix);
     }
   }
+  if (DO_BIN) {
+    const int nb = n + p.lookahead;  // same tile, `lookahead` frames on
+    if (tid == 0) s_on = 0;
+    __syncthreads();
+    if (nb < d.N) {
+      if (live) {
+        const float* fl = p.flow + (int64_t)nb * 2 * HW + pix;
+        const float bfx = __ldg(fl), bfy = __ldg(fl + HW);
+        const float bm = HAS_MASK ? __ldg(p.mask + (int64_t)nb * HW + pix) : 1.f;
+        const int64_t idx = (int64_t)nb * HW + pix;
+        if (bin_pixel(p, idx, nb, i, j, bfx, bfy, bm)) s_olist[atomicAdd(&s_on, 1)] = (int)idx;
+      }
+      __threadfence();  // this thread's list stores are visible device-wide before the tile is counted
+      __syncthreads();
+      const int nl = s_on;
+      if (tid == 0) {
+        if (nl) s_obase = atomicAdd(p.ovf_count, nl);
+        atomicAdd(p.done + nb, 1);
+      }
+      if (nl) {
+        __syncthreads();
+        for (int k = tid; k < nl; k += TH * TW) p.ovf_list[s_obase + k] = s_olist[k];
+      }
+    }
+    // the lists of frame n are complete once all its tiles have been counted
+    if (tid == 0 && n >= p.lookahead) {  // (the first `lookahead` frames were binned by the preceding launch)
+      const int want = tiles_x * tiles_y;
+      const volatile int* dn = p.done + n;
+      unsigned spins = 0;
+      while (*dn < want) {
+        __nanosleep(200);
+        if (++spins > (1u << 24)) __trap();  // never in practice: fail loudly rather than hang
+      }
+      __threadfence();
+    }
+    __syncthreads();
+  }
   if (DO_GX && live) {  // this pixel's contributor list (issued before the TMA wait so the two overlap)
     const int64_t ndest = (int64_t)HW * d.x_batch;
     const int64_t D = (int64_t)n * HW + pix;
-    const int c = min(__ldg(p.cnt + D), kListCap);
+    const int c = min(DO_BIN ? __ldcg(p.cnt + D) : __ldg(p.cnt + D), kListCap);
     const int self = (int)((uint32_t)D * (uint32_t)C4);  // a valid gout pixel for the padding entries
     const int4* ep = reinterpret_cast<const int4*>(p.entries) + D;
     int4 e[NP];
 #pragma unroll
     for (int k = 0; k < NP; ++k)
-      if (2 * k < c) e[k] = __ldg(ep + (int64_t)k * ndest);
+      if (2 * k < c) e[k] = DO_BIN ? __ldcg(ep + (int64_t)k * ndest) : __ldg(ep + (int64_t)k * ndest);
 #pragma unroll
     for (int k = 0; k < NP; ++k) {
       if (2 * k >= c) { e[k].x = self; e[k].y = 0; }
@@ -381,32 +446,47 @@ __global__ void __launch_bounds__(256, 3) gather_nhwc_kernel(const __grid_consta
   for (int s = 0; s < npx; s += G) {
     const int pa = s + grp;
     const bool act = (G == 1) || (pa < npx);
-    if (DO_GX && act) {
-      const int cnt = s_cnt[warp][pa];
-      const int4 e0 = s_ent[0][warp][pa], e1 = s_ent[1][warp][pa];
-      if (QI > 0) {
-        gx_pass<LP, (QI > 0 ? QI : 1)>(gl, gxl, cnt, e0, e1, &s_ent[2][warp][pa], &s_ent[3][warp][pa]);
-      } else {
+    constexpr int NQ = QI > 0 ? QI : 1;
+    float sa = 0.f, sb = 0.f, sc = 0.f, se = 0.f;  // sum_c gout[c] * x_corner[c]
+    if (QI > 0) {
+      // both roles' loads go out before the first use: one exposed memory latency per step, not two
+      int cnt = 0;
+      int4 e0 = make_int4(0, 0, 0, 0), e1 = e0;
+      float4 v[4][NQ];
+      DotRegs<NQ> dr;
+      if (act) {
+        if (DO_GX) {
+          cnt = s_cnt[warp][pa];
+          e0 = s_ent[0][warp][pa];
+          e1 = s_ent[1][warp][pa];
+          gx_issue<LP, NQ>(gl, cnt, e0, e1, v);
+        }
+        if (DO_GF) dot_issue<LP, NQ>(xl, gol, s_off[warp][pa], dr);
+        if (DO_GX) gx_finish<LP, NQ>(gl, gxl, cnt, e0, e1, &s_ent[2][warp][pa], &s_ent[3][warp][pa], v);
+        if (DO_GF) dot_finish<NQ>(dr, sa, sb, sc, se);
+      }
+    } else if (act) {
 #pragma unroll 1
-        for (int qi = 0; qi < nq; ++qi)
-          gx_pass<LP, 1>(gl + qi * (LP * 16), gxl + qi * (LP * 16), cnt, e0, e1, &s_ent[2][warp][pa], &s_ent[3][warp][pa]);
+      for (int qi = 0; qi < nq; ++qi) {
+        if (DO_GX) {
+          const int cnt = s_cnt[warp][pa];
+          const int4 e0 = s_ent[0][warp][pa], e1 = s_ent[1][warp][pa];
+          float4 v[4][1];
+          gx_issue<LP, 1>(gl + qi * (LP * 16), cnt, e0, e1, v);
+          gx_finish<LP, 1>(gl + qi * (LP * 16), gxl + qi * (LP * 16), cnt, e0, e1, &s_ent[2][warp][pa],
+                           &s_ent[3][warp][pa], v);
+        }
+        if (DO_GF) {
+          DotRegs<1> dr;
+          dot_issue<LP, 1>(xl + qi * (LP * 16), gol + qi * (LP * 16), s_off[warp][pa], dr);
+          dot_finish<1>(dr, sa, sb, sc, se);
+        }
       }
     }
     if (DO_GF) {
-      // sa..se = sum_c gout[c] * x_corner[c]: everything else is per-pixel algebra
-      float sa = 0.f, sb = 0.f, sc = 0.f, se = 0.f;
       const int pr = act ? pa : 0;
       const float2 mk = s_mk[warp][pr];
       const int ok = __float_as_int(mk.y);
-      if (act) {
-        const uint4 off = s_off[warp][pa];
-        if (QI > 0) {
-          dot_pass<LP, (QI > 0 ? QI : 1)>(xl, gol, off, sa, sb, sc, se);
-        } else {
-#pragma unroll 1
-          for (int qi = 0; qi < nq; ++qi) dot_pass<LP, 1>(xl + qi * (LP * 16), gol + qi * (LP * 16), off, sa, sb, sc, se);
-        }
-      }
       if (!(ok & 1)) sa = 0.f;  // corners outside the image contribute nothing (ATen within_bounds)
       if (!(ok & 2)) sb = 0.f;
       if (!(ok & 4)) sc = 0.f;
@@ -586,6 +666,7 @@ __global__ void __launch_bounds__(TH* TW, 2) gather_nchw_kernel(const __grid_con
 struct GatherWs {
   int* cnt;        // [x_batch*H*W] + the overflow-list length right behind it (one memset clears both)
   int* ovf_count;
+  int* done;       // [N] tiles binned per frame (fused binning), cleared by the same memset
   void* entries;
   unsigned char* ovf;
   int* ovf_list;
@@ -601,7 +682,8 @@ static GatherWs carve(void* base, int64_t N, int H, int W, int64_t x_batch) {
   size_t o = 0;
   w.cnt = reinterpret_cast<int*>(b + o);
   w.ovf_count = w.cnt + npix_d;
-  w.cnt_bytes = (npix_d + 1) * sizeof(int);
+  w.done = w.ovf_count + 1;
+  w.cnt_bytes = (npix_d + 1 + (size_t)N) * sizeof(int);
   o += up(w.cnt_bytes);
   w.entries = b + o;
   o += up(npix_d * kListCap * sizeof(ListEntry));
@@ -633,18 +715,17 @@ bool gather_supported(const BwdParams& p, Layout lx, Layout lg) {
   return true;
 }
 
-template <int LP, int QI, bool DO_GX, bool DO_GF>
+template <int LP, int QI, bool DO_GX, bool DO_GF, bool DO_BIN>
 static void launch_gather_nhwc(BwdParams p, cudaStream_t st) {
   p.pf_tiles = prefetch_tiles(0);  // measured: own tile, issued at CTA start, is the best distance
   constexpr int TH = 8, TW = 32;
   const Dims& d = p.d;
-  const int nimg = DO_GF ? d.N : d.x_batch;
-  const int tiles = nimg * ((d.H + TH - 1) / TH) * ((d.W + TW - 1) / TW);
+  const int tiles = p.nframes * ((d.H + TH - 1) / TH) * ((d.W + TW - 1) / TW);
   TileMaps tm;
   memset(&tm, 0, sizeof(tm));
   if (DO_GF) tm = make_tile_maps(d, p.flow, p.mask, TH, TW);
 #define C2M_LAUNCH(MASK, TMA) \
-  gather_nhwc_kernel<LP, QI, DO_GX, DO_GF, MASK, TMA><<<tiles, TH * TW, 0, st>>>(p, tm.flow, tm.mask)
+  gather_nhwc_kernel<LP, QI, DO_GX, DO_GF, MASK, TMA, DO_BIN><<<tiles, TH * TW, 0, st>>>(p, tm.flow, tm.mask)
   if (p.mask) {
     if (tm.ok) C2M_LAUNCH(true, true); else C2M_LAUNCH(true, false);
   } else {
@@ -654,23 +735,23 @@ static void launch_gather_nhwc(BwdParams p, cudaStream_t st) {
   count_launch();
 }
 
-template <bool DO_GX, bool DO_GF>
+template <bool DO_GX, bool DO_GF, bool DO_BIN = false>
 static void launch_gather_nhwc_lp(const BwdParams& p, cudaStream_t st) {
   const int C4 = p.d.C / 4;
   switch (C4) {  // two float4 groups per lane where C allows: half the per-pixel overhead of one
-    case 1: return launch_gather_nhwc<1, 1, DO_GX, DO_GF>(p, st);
-    case 2: return launch_gather_nhwc<1, 2, DO_GX, DO_GF>(p, st);
-    case 4: return launch_gather_nhwc<2, 2, DO_GX, DO_GF>(p, st);
-    case 8: return launch_gather_nhwc<4, 2, DO_GX, DO_GF>(p, st);
-    case 16: return launch_gather_nhwc<8, 2, DO_GX, DO_GF>(p, st);
-    case 32: return launch_gather_nhwc<16, 2, DO_GX, DO_GF>(p, st);
-    case 64: return launch_gather_nhwc<32, 2, DO_GX, DO_GF>(p, st);
+    case 1: return launch_gather_nhwc<1, 1, DO_GX, DO_GF, DO_BIN>(p, st);
+    case 2: return launch_gather_nhwc<1, 2, DO_GX, DO_GF, DO_BIN>(p, st);
+    case 4: return launch_gather_nhwc<2, 2, DO_GX, DO_GF, DO_BIN>(p, st);
+    case 8: return launch_gather_nhwc<4, 2, DO_GX, DO_GF, DO_BIN>(p, st);
+    case 16: return launch_gather_nhwc<8, 2, DO_GX, DO_GF, DO_BIN>(p, st);
+    case 32: return launch_gather_nhwc<16, 2, DO_GX, DO_GF, DO_BIN>(p, st);
+    case 64: return launch_gather_nhwc<32, 2, DO_GX, DO_GF, DO_BIN>(p, st);
     default: break;
   }
-  if (C4 >= 24) return launch_gather_nhwc<32, 0, DO_GX, DO_GF>(p, st);
-  if (C4 >= 12) return launch_gather_nhwc<16, 0, DO_GX, DO_GF>(p, st);
-  if (C4 >= 6) return launch_gather_nhwc<8, 0, DO_GX, DO_GF>(p, st);
-  return launch_gather_nhwc<4, 0, DO_GX, DO_GF>(p, st);
+  if (C4 >= 24) return launch_gather_nhwc<32, 0, DO_GX, DO_GF, DO_BIN>(p, st);
+  if (C4 >= 12) return launch_gather_nhwc<16, 0, DO_GX, DO_GF, DO_BIN>(p, st);
+  if (C4 >= 6) return launch_gather_nhwc<8, 0, DO_GX, DO_GF, DO_BIN>(p, st);
+  return launch_gather_nhwc<4, 0, DO_GX, DO_GF, DO_BIN>(p, st);
 }
 
 template <bool DO_GX, bool DO_GF, bool REPEAT>
@@ -705,11 +786,26 @@ static void launch_gather_nchw(BwdParams p, cudaStream_t st) {
   count_launch();
 }
 
+// Fused binning needs the CTAs that bin a frame to be long gone when that frame's own CTAs start:
+// look far enough ahead that two full waves of CTAs lie in between.
+static int bin_lookahead(const Dims& d) {
+  static const int off = [] {
+    const char* e = getenv("C2M_WARP_FUSED_BIN");
+    return e && *e ? (atoi(e) == 0) : 0;
+  }();
+  if (off) return 0;
+  const int tiles = ((d.H + 7) / 8) * ((d.W + 31) / 32);
+  const int la = (2 * 3 * sm_count() + tiles - 1) / tiles;
+  return (la >= 1 && 2 * la <= d.N) ? la : 0;  // too few frames to pipeline: separate bin launch
+}
+
 int launch_bwd_gather(const BwdParams& pin, Layout lx, void* workspace, size_t workspace_bytes, cudaStream_t st) {
   BwdParams p = pin;
   const Dims& d = p.d;
   const bool need_gf = p.gflow || p.gmask;
   const bool repeat = d.x_batch != d.N;
+  p.n0 = 0;
+  p.nframes = d.N;
   if (p.gx) {
     const GatherWs w = carve(workspace, d.N, d.H, d.W, d.x_batch);
     if (!workspace || workspace_bytes < w.bytes) {
@@ -721,22 +817,37 @@ int launch_bwd_gather(const BwdParams& pin, Layout lx, void* workspace, size_t w
     p.ovf = w.ovf;
     p.ovf_count = w.ovf_count;
     p.ovf_list = w.ovf_list;
+    p.done = w.done;
     p.key_mul = lx == LAYOUT_NHWC ? d.C / 4 : 1;  // channels-last lists address gout in 16-byte units
     if (cudaMemsetAsync(p.cnt, 0, w.cnt_bytes, st) != cudaSuccess) return C2M_ERR_CUDA;
-    const int64_t total = (int64_t)d.N * d.H * d.W;
-    bin_kernel<<<(unsigned)((total + kBinPixelsPerBlock - 1) / kBinPixelsPerBlock), 256, 0, st>>>(p);
-    count_launch();
   }
   const bool fuse = p.gx && need_gf && !repeat;
-  if (lx == LAYOUT_NHWC) {
-    if (fuse) {
-      launch_gather_nhwc_lp<true, true>(p, st);
-    } else {
-      if (p.gx) launch_gather_nhwc_lp<true, false>(p, st);
-      if (need_gf) launch_gather_nhwc_lp<false, true>(p, st);
-    }
+  auto bin = [&](int n0, int nf) {
+    BwdParams q = p;
+    q.n0 = n0;
+    q.nframes = nf;
+    const int64_t total = (int64_t)nf * d.H * d.W;
+    bin_kernel<<<(unsigned)((total + kBinPixelsPerBlock - 1) / kBinPixelsPerBlock), 256, 0, st>>>(q);
+    count_launch();
+  };
+  const int la = (lx == LAYOUT_NHWC && fuse) ? bin_lookahead(d) : 0;
+  if (la > 0) {
+    // frames 0 .. la-1 are binned up front, every later frame by the gather CTAs `la` frames before it
+    bin(0, la);
+    p.lookahead = la;
+    launch_gather_nhwc_lp<true, true, true>(p, st);
   } else {
-    if (fuse) {
+    if (p.gx) bin(0, d.N);
+    if (lx == LAYOUT_NHWC && fuse) {
+      launch_gather_nhwc_lp<true, true>(p, st);
+    } else if (lx == LAYOUT_NHWC) {
+      BwdParams q = p;
+      if (p.gx) {
+        q.nframes = d.x_batch;  // a grad-input-only pass walks the images of x
+        launch_gather_nhwc_lp<true, false>(q, st);
+      }
+      if (need_gf) launch_gather_nhwc_lp<false, true>(p, st);
+    } else if (fuse) {
       launch_gather_nchw<true, true, false>(p, st);
     } else {
       if (p.gx) {

@@ -123,6 +123,25 @@ __global__ void __launch_bounds__(256) kD(int* cnt, int* sink, float noise) {
   if (acc == -12345) sink[0] = 1;
 }
 
+// A + the 8-byte entry store at the claimed slot (list layout of the product: planes of entry pairs)
+template <int CAP, bool PLANES>
+__global__ void __launch_bounds__(256) kS(int* cnt, int2* ent, float noise) {
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < NPIX; idx += (long long)gridDim.x * blockDim.x) {
+    const int n = idx / HW, r = idx % HW, i = r / W, j = r % W;
+    int D[4];
+    dests(n, i, j, noise, D);
+    int s[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s[k] = atomicAdd(cnt + D[k], 1);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (s[k] < CAP) {
+        const long long slot = PLANES ? (((long long)(s[k] >> 1) * NPIX + D[k]) << 1) + (s[k] & 1) : (long long)D[k] * CAP + s[k];
+        ent[slot] = make_int2((int)idx, k);
+      }
+  }
+}
+
 template <class F>
 static float timeit(F f, int* cnt) {
   cudaEvent_t e0, e1;
@@ -146,12 +165,16 @@ int main() {
   CK(cudaMalloc(&cnt, NPIX * sizeof(int)));
   CK(cudaMalloc(&sink, 4));
   const int grid = 148 * 16, tiles = N * (H / 8) * (W / 32);
+  int2* ent;
+  CK(cudaMalloc(&ent, NPIX * 8 * sizeof(int2)));
   for (float noise : {0.f, 1.f}) {
     printf("noise %.0f px: %lld pixels, %lld claims\n", noise, NPIX, 4 * NPIX);
     printf("  A global returning atomics      %7.3f ms\n", timeit([&] { kA<<<grid, 256>>>(cnt, sink, noise); }, cnt));
     printf("  A' same, grid = all pixels      %7.3f ms\n", timeit([&] { kA<<<(unsigned)(NPIX / 256), 256>>>(cnt, sink, noise); }, cnt));
     printf("  B global reductions (no return) %7.3f ms\n", timeit([&] { kB<<<grid, 256>>>(cnt, noise); }, cnt));
     printf("  C 64-bit packed pairs           %7.3f ms\n", timeit([&] { kC<<<grid, 256>>>(cnt, sink, noise); }, cnt));
+    printf("  S atomics + entry store, planes %7.3f ms\n", timeit([&] { kS<8, true><<<grid, 256>>>(cnt, ent, noise); }, cnt));
+    printf("  S atomics + entry store, AoS    %7.3f ms\n", timeit([&] { kS<8, false><<<grid, 256>>>(cnt, ent, noise); }, cnt));
     printf("  D smem window + reservation     %7.3f ms\n", timeit([&] { kD<true><<<tiles, 256>>>(cnt, sink, noise); }, cnt));
     printf("  E smem window only              %7.3f ms\n", timeit([&] { kD<false><<<tiles, 256>>>(cnt, sink, noise); }, cnt));
   }
