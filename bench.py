@@ -6,7 +6,8 @@
 
 One step = one forward + one backward (grad-input, grad-flow, grad-mask) of the op over one batch
 of synthetic Cityscapes-shaped frames (BASELINE.json configs[1]: 8 clips x 5 frames = 40 frames,
-C=64, 256x512, fp32, NCHW).  A frame is one [C,H,W] slice of the folded batch x frame axis.
+C=64, 256x512, fp32; channels-last memory format by default -- the layout the sm_100a kernels are
+built around -- with the NCHW-contiguous figure reported beside it).  A frame is one [C,H,W] slice of the folded batch x frame axis.
 
 Prints ONE JSON line (rank 0).  Keys follow the driver's contract; see DESIGN.md "Measurement".
 """
@@ -236,9 +237,40 @@ def run_ours(args):
     value, ms_max, total_frames = cdist.aggregate_throughput(N * args.steps, ms_total, dev)
 
     # ---- end to end through the public API with HOST buffers (pinned), copies inside the timed region
+    # ---- secondary figure: the same step in the other memory format (not part of the timed region)
+    other = None
+    if not args.no_other_layout:
+        if nhwc:
+            x2, g2 = x.detach().contiguous().requires_grad_(True), gout.contiguous()
+        else:
+            x2 = x.detach().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+            g2 = gout.contiguous(memory_format=torch.channels_last)
+
+        def step2():
+            o = c2m_b200.warp_blend(x2, flow, mask, deterministic=det, flags=flags)
+            torch.autograd.grad(o, [x2, flow, mask], g2)
+
+        for _ in range(2):
+            step2()
+        barrier()
+        o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        o0.record()
+        for _ in range(3):
+            step2()
+        o1.record()
+        barrier()
+        oms = o0.elapsed_time(o1) / 3
+        oach = (fwd_bytes(N, C, H, W) + bwd_bytes(N, C, H, W)) / (oms * 1e-3) / 1e9
+        other = {"layout": "nchw" if nhwc else "nhwc", "ms_per_step": oms, "frames_per_s_per_gpu": N / (oms * 1e-3),
+                 "achieved": oach}
+        del x2, g2
+
     e2e = None
     if args.e2e_steps > 0:
         hx, hflow, hmask, hgout = synth(N, C, H, W, oob, 1234 + rank, dev, pin=True)
+        if nhwc:
+            hx = hx.contiguous(memory_format=torch.channels_last).pin_memory()
+            hgout = hgout.contiguous(memory_format=torch.channels_last).pin_memory()
         from c2m_b200 import host as chost
         plan = chost.HostWarpPlan(N, C, H, W, dev, chunks=args.e2e_chunks, nhwc=nhwc)
         e2e_steps = max(1, min(args.steps, args.e2e_steps))
@@ -268,6 +300,11 @@ def run_ours(args):
             "fwd_bwd": {"ms": fwd_ms + bwd_ms,
                         "achieved": (fwd_bytes(N, C, H, W) + bwd_bytes(N, C, H, W)) / ((fwd_ms + bwd_ms) * 1e-3) / 1e9}}
     roof["fwd_bwd"]["frac"] = roof["fwd_bwd"]["achieved"] / peak
+    roof["fwd"]["frac"] = roof["fwd"]["achieved"] / peak
+    roof["bwd"]["frac"] = roof["bwd"]["achieved"] / peak
+    if other is not None:
+        other["frac"] = other["achieved"] / peak
+        roof["other_layout"] = other
     tr = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tr):
         try:
@@ -310,7 +347,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cityscapes_256x512_c64", choices=sorted(WORKLOADS))
-    ap.add_argument("--layout", default="nchw", choices=["nchw", "nhwc"])
+    ap.add_argument("--layout", default="nhwc", choices=["nchw", "nhwc"],
+                    help="memory format of x / gout / out / gx (logical shape is always [N,C,H,W])")
+    ap.add_argument("--no-other-layout", action="store_true", help="skip the secondary (other layout) measurement")
     ap.add_argument("--frames", type=int, default=0, help="override frames per GPU")
     ap.add_argument("--deterministic", action="store_true")
     ap.add_argument("--flags", default="0")

@@ -38,13 +38,10 @@ class HostWarpPlan:
         self.gflow = torch.empty_like(self.flow)
         self.gmask = torch.empty_like(self.mask)
         pin = dict(dtype=torch.float32, pin_memory=True)
-        self.h_out = torch.empty((N, C, H, W), **pin)
-        self.h_gx = torch.empty((N, C, H, W), **pin)
+        self.h_out = torch.empty((N, C, H, W), memory_format=fmt, **pin)
+        self.h_gx = torch.empty((N, C, H, W), memory_format=fmt, **pin)
         self.h_gflow = torch.empty((N, 2, H, W), **pin)
         self.h_gmask = torch.empty((N, 1, H, W), **pin)
-        if nhwc:
-            self.h_out = self.h_out.contiguous(memory_format=fmt).pin_memory()
-            self.h_gx = self.h_gx.contiguous(memory_format=fmt).pin_memory()
         per = (N + self.chunks - 1) // self.chunks
         ws_bytes = _lib.bwd_workspace_bytes(per, C, H, W, per, True, self.flags)
         self.ws = [torch.empty(ws_bytes, dtype=torch.uint8, device=d) for _ in range(2)]

@@ -82,11 +82,13 @@ def test_argument_validation_happens_before_any_device_work():
 
 
 def test_workspace_size_contract():
-    # default (gather-form) backward: per destination pixel a 4 B counter + 8 in-line (src, w)
-    # entries, per output pixel a 1 B overflow flag, each block rounded up to 256 B
+    # default (gather-form) backward: per destination pixel a 4 B counter (+ the overflow-list length and
+    # one per-frame "tiles binned" counter behind the counters) and 8 in-line (src, w) entries; per output
+    # pixel a 1 B overflow flag and a 4 B overflow-list slot; each block rounded up to 256 B
     up = lambda v: (v + 255) // 256 * 256  # noqa: E731
     npix = 4 * 16 * 32
-    assert _lib.bwd_workspace_bytes(4, 8, 16, 32, 4, True, 0) == 256 + up(4 * npix) + up(64 * npix) + up(npix)
+    assert _lib.bwd_workspace_bytes(4, 8, 16, 32, 4, True, 0) == (
+        256 + up(4 * (npix + 1 + 4)) + up(64 * npix) + up(npix) + up(4 * npix))
     assert _lib.bwd_workspace_bytes(4, 8, 16, 32, 4, True, _lib.FLAG_BWD_ATOMIC) == 256
     det = _lib.bwd_workspace_bytes(4, 8, 16, 32, 4, True, _lib.FLAG_DETERMINISTIC)
     assert det == 256 + 4 * 8 * 16 * 32 * 8
