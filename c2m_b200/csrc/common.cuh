@@ -65,8 +65,10 @@ struct BwdParams {
   int* ovf_count;           // number of output pixels with a non-zero `ovf`
   int* ovf_list;            // their indices, in no particular order
   int n0, nframes;          // the frames [n0, n0 + nframes) a launch covers
-  int lookahead;            // fused binning: a gather CTA of frame n also bins its tile of frame n + lookahead
-  int* done;                // [N] tiles of frame n whose binning has completed (fused binning)
+  // channels-last local binning (no global contributor lists): candidate row segments per destination tile
+  int* tcnt;                // [x_batch * tiles] segments registered per destination tile
+  int* tlist;               // [x_batch * tiles][cand_cap] segment ids (n * H + i) * tiles_x + bx
+  int cand_cap;
   int key_mul;              // list entries name their source as pixel index * key_mul
   int pf_tiles;             // channels-last: L2 prefetch distance in tiles (< 0: off)
 };
@@ -305,7 +307,10 @@ __device__ __forceinline__ void store_geo(TileGeo<TP>& tg, int t, const Geo& g, 
 enum Layout { LAYOUT_NCHW = 0, LAYOUT_NHWC = 1, LAYOUT_OTHER = 2 };
 
 // Gather-form backward: contributor lists (one per destination pixel of grad-input)
-constexpr int kListCap = 8;  // in-line entries per destination; the tail goes through atomics
+constexpr int kListCap = 8;   // global lists (NCHW path): in-line entries per destination; the tail goes through atomics
+constexpr int kLocalCap = 12; // channels-last local binning: entries per destination in shared memory
+constexpr int kCandPerFrame = 96;  // candidate row segments a destination tile can register per source frame
+constexpr int kCandMax = 256;      // ... and in total (8 warps x 32 lanes preload the ids)
 struct ListEntry {
   int src;    // source (output) pixel n*H*W + i*W + j, times BwdParams::key_mul
   float w;    // bilinear weight * mask

@@ -19,6 +19,7 @@
 // out.  Extra traffic of this formulation: 4 B counter + 64 B list per destination pixel written and
 // read once, 1 B flag per output pixel -- about 1/6 of a C=64 pixel's bytes -- and no zero-fill,
 // no read-modify-write of grad-input.
+#include <climits>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -98,6 +99,92 @@ __global__ void __launch_bounds__(256) bin_kernel(const BwdParams p) {
   if (threadIdx.x == 0) s_base = atomicAdd(p.ovf_count, nl);
   __syncthreads();
   for (int k = threadIdx.x; k < nl; k += 256) p.ovf_list[s_base + k] = s_list[k];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Channels-last local binning, pass A.  One warp per row segment (32 consecutive output pixels of one image
+// row): the bounding box of the destination pixels its samples touch is turned into the set of 8 x 32
+// destination tiles it overlaps, and the segment registers itself as a candidate with each of them (one
+// global atomic per overlapped tile -- about 3 per 32 pixels instead of 4 per pixel).  The gather CTA of a
+// tile later recomputes the geometry of its candidates and builds the per-pixel lists in shared memory.
+// A segment whose box spans too many tiles (incoherent flow), or whose registration does not fit a tile's
+// candidate array, hands the affected contributions to overflow_kernel instead (flag byte + compact list).
+__global__ void __launch_bounds__(256) segbin_kernel(const BwdParams p) {
+  constexpr int TH = 8, TW = 32, kMaxCells = 12;
+  const Dims& d = p.d;
+  const int HW = d.H * d.W;
+  const int tiles_x = (d.W + TW - 1) / TW, tiles_y = (d.H + TH - 1) / TH;
+  const int lane = threadIdx.x & 31;
+  const int64_t nseg = (int64_t)d.N * d.H * tiles_x;
+  const int64_t seg = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (seg >= nseg) return;
+  const int bx = (int)(seg % tiles_x);
+  const int64_t r = seg / tiles_x;
+  const int i = (int)(r % d.H), n = (int)(r / d.H);
+  const int j = bx * TW + lane;
+  const bool live = j < d.W;
+  int xmin = INT_MAX, xmax = INT_MIN, ymin = INT_MAX, ymax = INT_MIN;
+  int ys[4] = {0, 0, 0, 0}, xs[4] = {0, 0, 0, 0};
+  bool act[4] = {false, false, false, false};
+  const int idx = n * HW + i * d.W + j;
+  if (live) {
+    const float* fl = p.flow + (int64_t)n * 2 * HW + i * d.W + j;
+    const float fx = __ldg(fl), fy = __ldg(fl + HW);
+    const float m = p.mask ? __ldg(p.mask + (int64_t)n * HW + i * d.W + j) : 1.f;
+    Geo g;
+    make_geo<true>(d, fx, fy, i, j, g);
+    ys[0] = ys[1] = g.y0; ys[2] = ys[3] = g.y1;
+    xs[0] = xs[2] = g.x0; xs[1] = xs[3] = g.x1;
+    act[0] = g.oknw && g.wnw * m != 0.f;
+    act[1] = g.okne && g.wne * m != 0.f;
+    act[2] = g.oksw && g.wsw * m != 0.f;
+    act[3] = g.okse && g.wse * m != 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (act[k]) {
+        xmin = min(xmin, xs[k]); xmax = max(xmax, xs[k]);
+        ymin = min(ymin, ys[k]); ymax = max(ymax, ys[k]);
+      }
+  }
+  xmin = __reduce_min_sync(0xffffffffu, xmin);
+  xmax = __reduce_max_sync(0xffffffffu, xmax);
+  ymin = __reduce_min_sync(0xffffffffu, ymin);
+  ymax = __reduce_max_sync(0xffffffffu, ymax);
+  if (xmax < xmin) return;  // nothing lands anywhere (all weights zero / out of bounds)
+  const int tx0 = xmin / TW, ty0 = ymin / TH;
+  const int ncols = xmax / TW - tx0 + 1, nrows = ymax / TH - ty0 + 1;
+  const int ncell = ncols * nrows;
+  unsigned fail;
+  if (ncell > kMaxCells) {
+    fail = 0xffffffffu;
+  } else {
+    bool ok = true;
+    if (lane < ncell) {
+      const int dt = ((n % d.x_batch) * tiles_y + ty0 + lane / ncols) * tiles_x + tx0 + lane % ncols;
+      const int slot = atomicAdd(p.tcnt + dt, 1);
+      if (slot < p.cand_cap) p.tlist[(int64_t)dt * p.cand_cap + slot] = (int)seg;
+      else ok = false;
+    }
+    fail = __ballot_sync(0xffffffffu, !ok);
+  }
+  if (fail == 0u) return;
+  unsigned ovf = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (act[k]) {
+      const int cell = (ys[k] / TH - ty0) * ncols + (xs[k] / TW - tx0);
+      if (fail == 0xffffffffu || ((fail >> cell) & 1u)) ovf |= 1u << k;
+    }
+  // each pixel belongs to exactly one segment and no gather CTA runs yet: a plain byte store is race free
+  const unsigned has = __ballot_sync(0xffffffffu, ovf != 0u);
+  if (has == 0u) return;
+  int base = 0;
+  if (lane == __ffs(has) - 1) base = atomicAdd(p.ovf_count, __popc(has));
+  base = __shfl_sync(0xffffffffu, base, __ffs(has) - 1);
+  if (ovf) {
+    p.ovf[idx] = (unsigned char)ovf;
+    p.ovf_list[base + __popc(has & ((1u << lane) - 1u))] = idx;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -216,9 +303,11 @@ __device__ __forceinline__ void gx_issue(const char* gl, int cnt, const int4& e0
   }
 }
 
-template <int LP, int NQ>
+// `ent` points at pair 0 of this destination's list in shared memory, consecutive pairs `pstride` int4 apart;
+// NP pairs in all (pairs 0 and 1 arrive in e0 / e1, already loaded).
+template <int LP, int NQ, int NP>
 __device__ __forceinline__ void gx_finish(const char* gl, char* po, int cnt, const int4& e0, const int4& e1,
-                                          const int4* ent2, const int4* ent3, const float4 (&v)[4][NQ]) {
+                                          const int4* ent, int pstride, const float4 (&v)[4][NQ]) {
   const float w0 = __int_as_float(e0.y), w1 = __int_as_float(e0.w);
   const float w2 = __int_as_float(e1.y), w3 = __int_as_float(e1.w);
   float4 acc[NQ];
@@ -229,20 +318,21 @@ __device__ __forceinline__ void gx_finish(const char* gl, char* po, int cnt, con
     acc[q].z = fmaf(w3, v[3][q].z, fmaf(w2, v[2][q].z, fmaf(w1, v[1][q].z, w0 * v[0][q].z)));
     acc[q].w = fmaf(w3, v[3][q].w, fmaf(w2, v[2][q].w, fmaf(w1, v[1][q].w, w0 * v[0][q].w)));
   }
-  if (cnt > 4) {  // long list: entries 4..7, two at a time (slots past the count hold weight 0)
+  if (cnt > 4) {  // long list: two entries at a time
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      if (k == 0 || cnt > 6) {
-        const int4 e = k == 0 ? *ent2 : *ent3;
+    for (int k = 2; k < NP; ++k) {
+      if (cnt > 2 * k) {
+        const int4 e = ent[k * pstride];
         const float4* b0 = key_ptr(gl, e.x);
         const float4* b1 = key_ptr(gl, e.z);
+        const bool two = cnt > 2 * k + 1;
         float4 u[2][NQ];
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
           u[0][q] = ldg_batch(b0 + q * LP);
-          u[1][q] = ldg_batch_if(b1 + q * LP, cnt > 5 + 2 * k);
+          u[1][q] = ldg_batch_if(b1 + q * LP, two);
         }
-        const float wa = __int_as_float(e.y), wb = __int_as_float(e.w);
+        const float wa = __int_as_float(e.y), wb = two ? __int_as_float(e.w) : 0.f;
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
           acc[q].x = fmaf(wb, u[1][q].x, fmaf(wa, u[0][q].x, acc[q].x));
@@ -288,19 +378,17 @@ __device__ __forceinline__ void dot_finish(const DotRegs<NQ>& r, float& sa, floa
 
 //   LP  lanes per pixel (a warp moves 32/LP pixels side by side)
 //   QI  float4 groups per lane when C/4 == LP*QI exactly, 0 = run-time channel loop
-//   DO_BIN  fused binning: the CTA of (frame n, tile t) first bins tile t of frame n + lookahead (the slot
-//           claims and list stores then overlap the bandwidth-bound streaming of other CTAs instead of
-//           occupying a launch of their own); a frame's lists are read only once every tile of it has
-//           been binned, which -- CTAs being dispatched in index order -- earlier CTAs of this launch
-//           (or the preceding bin_kernel launch) have long done.
-template <int LP, int QI, bool DO_GX, bool DO_GF, bool HAS_MASK, bool USE_TMA, bool DO_BIN>
+//   LOCAL   the contributor lists are built by the CTA itself in shared memory from the row segments that
+//           segbin_kernel registered as candidates for this destination tile (no global lists, no global
+//           atomics per contribution); otherwise they are read from the global lists bin_kernel wrote.
+template <int LP, int QI, bool DO_GX, bool DO_GF, bool HAS_MASK, bool USE_TMA, bool LOCAL>
 __global__ void __launch_bounds__(256, 3) gather_nhwc_kernel(const __grid_constant__ BwdParams p,
                                                              const __grid_constant__ CUtensorMap tm_flow,
                                                              const __grid_constant__ CUtensorMap tm_mask) {
   constexpr int TH = 8, TW = 32;
   constexpr int G = 32 / LP;
-  constexpr int NP = kListCap / 2;  // int4 entry pairs per destination
-  static_assert(NP == 4, "phase 1 is written for an eight-entry list");
+  constexpr int CAP = LOCAL ? kLocalCap : kListCap;  // entries per destination held in shared memory
+  constexpr int NP = CAP / 2;                        // as int4 entry pairs
   __shared__ alignas(128) float s_flow[DO_GF ? 2 : 1][TH][TW];
   __shared__ alignas(128) float s_mask[TH][TW];
   __shared__ alignas(8) uint64_t bar;
@@ -310,8 +398,6 @@ __global__ void __launch_bounds__(256, 3) gather_nhwc_kernel(const __grid_consta
   __shared__ float2 s_mk[DO_GF ? TH : 1][TW];   // mask value, in-bounds bits
   __shared__ int s_cnt[DO_GX ? TH : 1][TW];
   __shared__ int4 s_ent[DO_GX ? NP : 1][DO_GX ? TH : 1][TW];
-  __shared__ int s_olist[DO_BIN ? TH * TW : 1];  // pixels binned by this CTA whose list overflowed
-  __shared__ int s_on, s_obase;
   const Dims& d = p.d;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tiles_x = (d.W + TW - 1) / TW, tiles_y = (d.H + TH - 1) / TH;
@@ -360,60 +446,87 @@ __global__ void __launch_bounds__(256, 3) gather_nhwc_kernel(const __grid_consta
       if (HAS_MASK) m = __ldg(p.mask + (int64_t)n * HW + pix);
     }
   }
-  if (DO_BIN) {
-    const int nb = n + p.lookahead;  // same tile, `lookahead` frames on
-    if (tid == 0) s_on = 0;
+  if (LOCAL && DO_GX) {
+    // ---- local binning: every warp walks candidate row segments (32 output pixels each), recomputes their
+    // geometry and files the contributions that land inside this tile into the destination's list
+    s_cnt[warp][lane] = 0;
     __syncthreads();
-    if (nb < d.N) {
-      if (live) {
-        const float* fl = p.flow + (int64_t)nb * 2 * HW + pix;
-        const float bfx = __ldg(fl), bfy = __ldg(fl + HW);
-        const float bm = HAS_MASK ? __ldg(p.mask + (int64_t)nb * HW + pix) : 1.f;
-        const int64_t idx = (int64_t)nb * HW + pix;
-        if (bin_pixel(p, idx, nb, i, j, bfx, bfy, bm)) s_olist[atomicAdd(&s_on, 1)] = (int)idx;
+    const int T = (n * tiles_y + by) * tiles_x + bx;  // destination tile (n: image of x)
+    const int ncand = min(__ldg(p.tcnt + T), p.cand_cap);
+    const int* tl = p.tlist + (int64_t)T * p.cand_cap;
+    const int myid = (warp + 8 * lane < ncand) ? __ldg(tl + warp + 8 * lane) : 0;  // warp w takes c = w, w+8, ...
+    const int nit = (ncand - warp + 7) >> 3;
+#pragma unroll 2
+    for (int it = 0; it < nit; ++it) {
+      const int seg = __shfl_sync(0xffffffffu, myid, it);
+      const int sbx = seg % tiles_x;
+      const int sr = seg / tiles_x;
+      const int si = sr % d.H, sn = sr / d.H;
+      const int sj = sbx * TW + lane;
+      if (sj < d.W) {
+        const int spix = si * d.W + sj;
+        const float* fl = p.flow + (int64_t)sn * 2 * HW + spix;
+        const float sfx = __ldg(fl), sfy = __ldg(fl + HW);
+        const float sm = HAS_MASK ? __ldg(p.mask + (int64_t)sn * HW + spix) : 1.f;
+        Geo g;
+        make_geo<true>(d, sfx, sfy, si, sj, g);
+        const int ys[4] = {g.y0, g.y0, g.y1, g.y1};
+        const int xs[4] = {g.x0, g.x1, g.x0, g.x1};
+        const float ws[4] = {g.wnw * sm, g.wne * sm, g.wsw * sm, g.wse * sm};
+        const bool oks[4] = {g.oknw, g.okne, g.oksw, g.okse};
+        const int sidx = sn * HW + spix;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const unsigned dy = (unsigned)(ys[k] - by * TH), dx = (unsigned)(xs[k] - bx * TW);
+          if (oks[k] && ws[k] != 0.f && dy < (unsigned)TH && dx < (unsigned)TW) {
+            const int slot = atomicAdd(&s_cnt[dy][dx], 1);
+            if (slot < CAP) {
+              reinterpret_cast<int2*>(&s_ent[slot >> 1][dy][dx])[slot & 1] =
+                  make_int2((int)((uint32_t)sidx * (uint32_t)C4), __float_as_int(ws[k]));
+            } else {
+              // list full: hand the contribution to overflow_kernel (flag byte per output pixel, shared
+              // with other tiles' overflows of the same pixel -> word-wide atomic OR)
+              unsigned* word = reinterpret_cast<unsigned*>(p.ovf) + (sidx >> 2);
+              const int sh = (sidx & 3) * 8;
+              const unsigned old = atomicOr(word, (1u << k) << sh);
+              if (((old >> sh) & 0xffu) == 0u) p.ovf_list[atomicAdd(p.ovf_count, 1)] = sidx;
+            }
+          }
+        }
       }
-      __threadfence();  // this thread's list stores are visible device-wide before the tile is counted
-      __syncthreads();
-      const int nl = s_on;
-      if (tid == 0) {
-        if (nl) s_obase = atomicAdd(p.ovf_count, nl);
-        atomicAdd(p.done + nb, 1);
-      }
-      if (nl) {
-        __syncthreads();
-        for (int k = tid; k < nl; k += TH * TW) p.ovf_list[s_obase + k] = s_olist[k];
-      }
-    }
-    // the lists of frame n are complete once all its tiles have been counted
-    if (tid == 0 && n >= p.lookahead) {  // (the first `lookahead` frames were binned by the preceding launch)
-      const int want = tiles_x * tiles_y;
-      const volatile int* dn = p.done + n;
-      unsigned spins = 0;
-      while (*dn < want) {
-        __nanosleep(200);
-        if (++spins > (1u << 24)) __trap();  // never in practice: fail loudly rather than hang
-      }
-      __threadfence();
     }
     __syncthreads();
   }
-  if (DO_GX && live) {  // this pixel's contributor list (issued before the TMA wait so the two overlap)
-    const int64_t ndest = (int64_t)HW * d.x_batch;
-    const int64_t D = (int64_t)n * HW + pix;
-    const int c = min(DO_BIN ? __ldcg(p.cnt + D) : __ldg(p.cnt + D), kListCap);
-    const int self = (int)((uint32_t)D * (uint32_t)C4);  // a valid gout pixel for the padding entries
-    const int4* ep = reinterpret_cast<const int4*>(p.entries) + D;
-    int4 e[NP];
+  if (DO_GX && live) {
+    const int self = (int)(((uint32_t)n * (uint32_t)HW + (uint32_t)pix) * (uint32_t)C4);  // a valid gout pixel for padding
+    if (LOCAL) {
+      // clamp the count, pad the first four slots with (own pixel, weight 0): phase 1 then needs no branch there
+      const int c = min(s_cnt[warp][lane], CAP);
 #pragma unroll
-    for (int k = 0; k < NP; ++k)
-      if (2 * k < c) e[k] = DO_BIN ? __ldcg(ep + (int64_t)k * ndest) : __ldg(ep + (int64_t)k * ndest);
+      for (int k = 0; k < 2; ++k) {
+        int4 e = s_ent[k][warp][lane];
+        if (2 * k >= c) { e.x = self; e.y = 0; }
+        if (2 * k + 1 >= c) { e.z = self; e.w = 0; }
+        s_ent[k][warp][lane] = e;
+      }
+      s_cnt[warp][lane] = c;
+    } else {  // global lists (issued before the TMA wait so the two overlap)
+      const int64_t ndest = (int64_t)HW * d.x_batch;
+      const int64_t D = (int64_t)n * HW + pix;
+      const int c = min(__ldg(p.cnt + D), kListCap);
+      const int4* ep = reinterpret_cast<const int4*>(p.entries) + D;
+      int4 e[NP];
 #pragma unroll
-    for (int k = 0; k < NP; ++k) {
-      if (2 * k >= c) { e[k].x = self; e[k].y = 0; }
-      if (2 * k + 1 >= c) { e[k].z = self; e[k].w = 0; }
-      if (k < 2 || 2 * k < c) s_ent[k][warp][lane] = e[k];
+      for (int k = 0; k < NP; ++k)
+        if (2 * k < c) e[k] = __ldg(ep + (int64_t)k * ndest);
+#pragma unroll
+      for (int k = 0; k < NP; ++k) {
+        if (2 * k >= c) { e[k].x = self; e[k].y = 0; }
+        if (2 * k + 1 >= c) { e[k].z = self; e[k].w = 0; }
+        if (k < 2 || 2 * k < c) s_ent[k][warp][lane] = e[k];
+      }
+      s_cnt[warp][lane] = c;
     }
-    s_cnt[warp][lane] = c;
   }
   if (DO_GF && USE_TMA) {
     mbar_wait(&bar, 0);
@@ -462,7 +575,7 @@ __global__ void __launch_bounds__(256, 3) gather_nhwc_kernel(const __grid_consta
           gx_issue<LP, NQ>(gl, cnt, e0, e1, v);
         }
         if (DO_GF) dot_issue<LP, NQ>(xl, gol, s_off[warp][pa], dr);
-        if (DO_GX) gx_finish<LP, NQ>(gl, gxl, cnt, e0, e1, &s_ent[2][warp][pa], &s_ent[3][warp][pa], v);
+        if (DO_GX) gx_finish<LP, NQ, NP>(gl, gxl, cnt, e0, e1, &s_ent[0][warp][pa], TH * TW, v);
         if (DO_GF) dot_finish<NQ>(dr, sa, sb, sc, se);
       }
     } else if (act) {
@@ -473,8 +586,7 @@ __global__ void __launch_bounds__(256, 3) gather_nhwc_kernel(const __grid_consta
           const int4 e0 = s_ent[0][warp][pa], e1 = s_ent[1][warp][pa];
           float4 v[4][1];
           gx_issue<LP, 1>(gl + qi * (LP * 16), cnt, e0, e1, v);
-          gx_finish<LP, 1>(gl + qi * (LP * 16), gxl + qi * (LP * 16), cnt, e0, e1, &s_ent[2][warp][pa],
-                           &s_ent[3][warp][pa], v);
+          gx_finish<LP, 1, NP>(gl + qi * (LP * 16), gxl + qi * (LP * 16), cnt, e0, e1, &s_ent[0][warp][pa], TH * TW, v);
         }
         if (DO_GF) {
           DotRegs<1> dr;
@@ -666,7 +778,6 @@ __global__ void __launch_bounds__(TH* TW, 2) gather_nchw_kernel(const __grid_con
 struct GatherWs {
   int* cnt;        // [x_batch*H*W] + the overflow-list length right behind it (one memset clears both)
   int* ovf_count;
-  int* done;       // [N] tiles binned per frame (fused binning), cleared by the same memset
   void* entries;
   unsigned char* ovf;
   int* ovf_list;
@@ -674,29 +785,65 @@ struct GatherWs {
   size_t bytes;
 };
 
+static size_t up256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+// global-list scheme (NCHW kernels)
 static GatherWs carve(void* base, int64_t N, int H, int W, int64_t x_batch) {
   const size_t npix_d = (size_t)x_batch * H * W, npix_o = (size_t)N * H * W;
-  auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
   GatherWs w;
   char* b = reinterpret_cast<char*>(base);
   size_t o = 0;
   w.cnt = reinterpret_cast<int*>(b + o);
   w.ovf_count = w.cnt + npix_d;
-  w.done = w.ovf_count + 1;
-  w.cnt_bytes = (npix_d + 1 + (size_t)N) * sizeof(int);
-  o += up(w.cnt_bytes);
+  w.cnt_bytes = (npix_d + 1) * sizeof(int);
+  o += up256(w.cnt_bytes);
   w.entries = b + o;
-  o += up(npix_d * kListCap * sizeof(ListEntry));
+  o += up256(npix_d * kListCap * sizeof(ListEntry));
   w.ovf = reinterpret_cast<unsigned char*>(b + o);
-  o += up(npix_o);
+  o += up256(npix_o);
   w.ovf_list = reinterpret_cast<int*>(b + o);
-  o += up(npix_o * sizeof(int));
+  o += up256(npix_o * sizeof(int));
   w.bytes = o;
   return w;
 }
 
+// local-binning scheme (channels-last kernels): [tcnt | ovf_count | ovf flags] are cleared by one memset
+struct LocalWs {
+  int* tcnt;
+  int* ovf_count;
+  unsigned char* ovf;
+  int* tlist;
+  int* ovf_list;
+  int cand_cap;
+  size_t clear_bytes;
+  size_t bytes;
+};
+
+static LocalWs carve_local(void* base, int64_t N, int H, int W, int64_t x_batch) {
+  const size_t ntile = (size_t)x_batch * ((H + 7) / 8) * ((W + 31) / 32), npix_o = (size_t)N * H * W;
+  LocalWs w;
+  int64_t cap = (int64_t)kCandPerFrame * (x_batch > 0 ? N / x_batch : 1);
+  w.cand_cap = (int)(cap > kCandMax ? kCandMax : cap);
+  char* b = reinterpret_cast<char*>(base);
+  size_t o = 0;
+  w.tcnt = reinterpret_cast<int*>(b + o);
+  w.ovf_count = w.tcnt + ntile;
+  o += up256((ntile + 1) * sizeof(int));
+  w.ovf = reinterpret_cast<unsigned char*>(b + o);
+  o += up256(npix_o);
+  w.clear_bytes = o;
+  w.tlist = reinterpret_cast<int*>(b + o);
+  o += up256(ntile * w.cand_cap * sizeof(int));
+  w.ovf_list = reinterpret_cast<int*>(b + o);
+  o += up256(npix_o * sizeof(int));
+  w.bytes = o;
+  return w;
+}
+
+// the caller does not tell the layout when it asks: size for the larger (global-list) scheme
 size_t gather_workspace_bytes(int64_t N, int H, int W, int64_t x_batch) {
-  return carve(nullptr, N, H, W, x_batch).bytes;
+  const size_t a = carve(nullptr, N, H, W, x_batch).bytes, b = carve_local(nullptr, N, H, W, x_batch).bytes;
+  return a > b ? a : b;
 }
 
 bool gather_supported(const BwdParams& p, Layout lx, Layout lg) {
@@ -715,7 +862,7 @@ bool gather_supported(const BwdParams& p, Layout lx, Layout lg) {
   return true;
 }
 
-template <int LP, int QI, bool DO_GX, bool DO_GF, bool DO_BIN>
+template <int LP, int QI, bool DO_GX, bool DO_GF, bool LOCAL>
 static void launch_gather_nhwc(BwdParams p, cudaStream_t st) {
   p.pf_tiles = prefetch_tiles(0);  // measured: own tile, issued at CTA start, is the best distance
   constexpr int TH = 8, TW = 32;
@@ -725,7 +872,7 @@ static void launch_gather_nhwc(BwdParams p, cudaStream_t st) {
   memset(&tm, 0, sizeof(tm));
   if (DO_GF) tm = make_tile_maps(d, p.flow, p.mask, TH, TW);
 #define C2M_LAUNCH(MASK, TMA) \
-  gather_nhwc_kernel<LP, QI, DO_GX, DO_GF, MASK, TMA, DO_BIN><<<tiles, TH * TW, 0, st>>>(p, tm.flow, tm.mask)
+  gather_nhwc_kernel<LP, QI, DO_GX, DO_GF, MASK, TMA, LOCAL><<<tiles, TH * TW, 0, st>>>(p, tm.flow, tm.mask)
   if (p.mask) {
     if (tm.ok) C2M_LAUNCH(true, true); else C2M_LAUNCH(true, false);
   } else {
@@ -735,23 +882,23 @@ static void launch_gather_nhwc(BwdParams p, cudaStream_t st) {
   count_launch();
 }
 
-template <bool DO_GX, bool DO_GF, bool DO_BIN = false>
+template <bool DO_GX, bool DO_GF, bool LOCAL>
 static void launch_gather_nhwc_lp(const BwdParams& p, cudaStream_t st) {
   const int C4 = p.d.C / 4;
   switch (C4) {  // two float4 groups per lane where C allows: half the per-pixel overhead of one
-    case 1: return launch_gather_nhwc<1, 1, DO_GX, DO_GF, DO_BIN>(p, st);
-    case 2: return launch_gather_nhwc<1, 2, DO_GX, DO_GF, DO_BIN>(p, st);
-    case 4: return launch_gather_nhwc<2, 2, DO_GX, DO_GF, DO_BIN>(p, st);
-    case 8: return launch_gather_nhwc<4, 2, DO_GX, DO_GF, DO_BIN>(p, st);
-    case 16: return launch_gather_nhwc<8, 2, DO_GX, DO_GF, DO_BIN>(p, st);
-    case 32: return launch_gather_nhwc<16, 2, DO_GX, DO_GF, DO_BIN>(p, st);
-    case 64: return launch_gather_nhwc<32, 2, DO_GX, DO_GF, DO_BIN>(p, st);
+    case 1: return launch_gather_nhwc<1, 1, DO_GX, DO_GF, LOCAL>(p, st);
+    case 2: return launch_gather_nhwc<1, 2, DO_GX, DO_GF, LOCAL>(p, st);
+    case 4: return launch_gather_nhwc<2, 2, DO_GX, DO_GF, LOCAL>(p, st);
+    case 8: return launch_gather_nhwc<4, 2, DO_GX, DO_GF, LOCAL>(p, st);
+    case 16: return launch_gather_nhwc<8, 2, DO_GX, DO_GF, LOCAL>(p, st);
+    case 32: return launch_gather_nhwc<16, 2, DO_GX, DO_GF, LOCAL>(p, st);
+    case 64: return launch_gather_nhwc<32, 2, DO_GX, DO_GF, LOCAL>(p, st);
     default: break;
   }
-  if (C4 >= 24) return launch_gather_nhwc<32, 0, DO_GX, DO_GF, DO_BIN>(p, st);
-  if (C4 >= 12) return launch_gather_nhwc<16, 0, DO_GX, DO_GF, DO_BIN>(p, st);
-  if (C4 >= 6) return launch_gather_nhwc<8, 0, DO_GX, DO_GF, DO_BIN>(p, st);
-  return launch_gather_nhwc<4, 0, DO_GX, DO_GF, DO_BIN>(p, st);
+  if (C4 >= 24) return launch_gather_nhwc<32, 0, DO_GX, DO_GF, LOCAL>(p, st);
+  if (C4 >= 12) return launch_gather_nhwc<16, 0, DO_GX, DO_GF, LOCAL>(p, st);
+  if (C4 >= 6) return launch_gather_nhwc<8, 0, DO_GX, DO_GF, LOCAL>(p, st);
+  return launch_gather_nhwc<4, 0, DO_GX, DO_GF, LOCAL>(p, st);
 }
 
 template <bool DO_GX, bool DO_GF, bool REPEAT>
@@ -786,17 +933,12 @@ static void launch_gather_nchw(BwdParams p, cudaStream_t st) {
   count_launch();
 }
 
-// Fused binning needs the CTAs that bin a frame to be long gone when that frame's own CTAs start:
-// look far enough ahead that two full waves of CTAs lie in between.
-static int bin_lookahead(const Dims& d) {
-  static const int off = [] {
-    const char* e = getenv("C2M_WARP_FUSED_BIN");
-    return e && *e ? (atoi(e) == 0) : 0;
+static bool use_local_binning() {
+  static const bool v = [] {
+    const char* e = getenv("C2M_WARP_BWD_LISTS");  // tuning hook: 1 = global contributor lists also for channels-last
+    return !(e && *e && atoi(e) != 0);
   }();
-  if (off) return 0;
-  const int tiles = ((d.H + 7) / 8) * ((d.W + 31) / 32);
-  const int la = (2 * 3 * sm_count() + tiles - 1) / tiles;
-  return (la >= 1 && 2 * la <= d.N) ? la : 0;  // too few frames to pipeline: separate bin launch
+  return v;
 }
 
 int launch_bwd_gather(const BwdParams& pin, Layout lx, void* workspace, size_t workspace_bytes, cudaStream_t st) {
@@ -804,9 +946,28 @@ int launch_bwd_gather(const BwdParams& pin, Layout lx, void* workspace, size_t w
   const Dims& d = p.d;
   const bool need_gf = p.gflow || p.gmask;
   const bool repeat = d.x_batch != d.N;
+  const bool fuse = p.gx && need_gf && !repeat;
+  const bool local = lx == LAYOUT_NHWC && use_local_binning();
   p.n0 = 0;
   p.nframes = d.N;
-  if (p.gx) {
+  p.key_mul = lx == LAYOUT_NHWC ? d.C / 4 : 1;  // channels-last lists address gout in 16-byte units
+  if (p.gx && local) {
+    const LocalWs w = carve_local(workspace, d.N, d.H, d.W, d.x_batch);
+    if (!workspace || workspace_bytes < w.bytes) {
+      set_error("workspace too small: %zu < %zu", workspace_bytes, w.bytes);
+      return C2M_ERR_WORKSPACE;
+    }
+    p.tcnt = w.tcnt;
+    p.tlist = w.tlist;
+    p.cand_cap = w.cand_cap;
+    p.ovf = w.ovf;
+    p.ovf_count = w.ovf_count;
+    p.ovf_list = w.ovf_list;
+    if (cudaMemsetAsync(w.tcnt, 0, w.clear_bytes, st) != cudaSuccess) return C2M_ERR_CUDA;
+    const int64_t nseg = (int64_t)d.N * d.H * ((d.W + 31) / 32);
+    segbin_kernel<<<(unsigned)((nseg + 7) / 8), 256, 0, st>>>(p);
+    count_launch();
+  } else if (p.gx) {
     const GatherWs w = carve(workspace, d.N, d.H, d.W, d.x_batch);
     if (!workspace || workspace_bytes < w.bytes) {
       set_error("workspace too small: %zu < %zu", workspace_bytes, w.bytes);
@@ -817,45 +978,37 @@ int launch_bwd_gather(const BwdParams& pin, Layout lx, void* workspace, size_t w
     p.ovf = w.ovf;
     p.ovf_count = w.ovf_count;
     p.ovf_list = w.ovf_list;
-    p.done = w.done;
-    p.key_mul = lx == LAYOUT_NHWC ? d.C / 4 : 1;  // channels-last lists address gout in 16-byte units
     if (cudaMemsetAsync(p.cnt, 0, w.cnt_bytes, st) != cudaSuccess) return C2M_ERR_CUDA;
-  }
-  const bool fuse = p.gx && need_gf && !repeat;
-  auto bin = [&](int n0, int nf) {
-    BwdParams q = p;
-    q.n0 = n0;
-    q.nframes = nf;
-    const int64_t total = (int64_t)nf * d.H * d.W;
-    bin_kernel<<<(unsigned)((total + kBinPixelsPerBlock - 1) / kBinPixelsPerBlock), 256, 0, st>>>(q);
+    const int64_t total = (int64_t)d.N * d.H * d.W;
+    bin_kernel<<<(unsigned)((total + kBinPixelsPerBlock - 1) / kBinPixelsPerBlock), 256, 0, st>>>(p);
     count_launch();
-  };
-  const int la = (lx == LAYOUT_NHWC && fuse) ? bin_lookahead(d) : 0;
-  if (la > 0) {
-    // frames 0 .. la-1 are binned up front, every later frame by the gather CTAs `la` frames before it
-    bin(0, la);
-    p.lookahead = la;
-    launch_gather_nhwc_lp<true, true, true>(p, st);
-  } else {
-    if (p.gx) bin(0, d.N);
-    if (lx == LAYOUT_NHWC && fuse) {
-      launch_gather_nhwc_lp<true, true>(p, st);
-    } else if (lx == LAYOUT_NHWC) {
-      BwdParams q = p;
-      if (p.gx) {
-        q.nframes = d.x_batch;  // a grad-input-only pass walks the images of x
-        launch_gather_nhwc_lp<true, false>(q, st);
+  }
+  if (lx == LAYOUT_NHWC) {
+    BwdParams q = p;
+    q.nframes = d.x_batch;  // a grad-input-only pass walks the images of x
+    if (local) {
+      if (fuse) {
+        launch_gather_nhwc_lp<true, true, true>(p, st);
+      } else {
+        if (p.gx) launch_gather_nhwc_lp<true, false, true>(q, st);
+        if (need_gf) launch_gather_nhwc_lp<false, true, false>(p, st);
       }
-      if (need_gf) launch_gather_nhwc_lp<false, true>(p, st);
-    } else if (fuse) {
-      launch_gather_nchw<true, true, false>(p, st);
     } else {
-      if (p.gx) {
-        if (repeat) launch_gather_nchw<true, false, true>(p, st);
-        else launch_gather_nchw<true, false, false>(p, st);
+      if (fuse) {
+        launch_gather_nhwc_lp<true, true, false>(p, st);
+      } else {
+        if (p.gx) launch_gather_nhwc_lp<true, false, false>(q, st);
+        if (need_gf) launch_gather_nhwc_lp<false, true, false>(p, st);
       }
-      if (need_gf) launch_gather_nchw<false, true, false>(p, st);
     }
+  } else if (fuse) {
+    launch_gather_nchw<true, true, false>(p, st);
+  } else {
+    if (p.gx) {
+      if (repeat) launch_gather_nchw<true, false, true>(p, st);
+      else launch_gather_nchw<true, false, false>(p, st);
+    }
+    if (need_gf) launch_gather_nchw<false, true, false>(p, st);
   }
   if (p.gx) {
     const int grid = sm_count() * 8;
