@@ -69,6 +69,8 @@ struct BwdParams {
   int* tcnt;                // [x_batch * tiles] segments registered per destination tile
   int* tlist;               // [x_batch * tiles][cand_cap] segment ids (n * H + i) * tiles_x + bx
   int cand_cap;
+  int4* pixrec;             // [N*H*W] per output pixel: (x0 | y0 << 16, ax, ay, mask) -- the sampling geometry,
+                            // computed once by segbin_kernel and reused by every tile that bins the pixel
   int key_mul;              // list entries name their source as pixel index * key_mul
   int pf_tiles;             // channels-last: L2 prefetch distance in tiles (< 0: off)
 };

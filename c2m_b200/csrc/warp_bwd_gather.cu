@@ -135,6 +135,11 @@ __global__ void __launch_bounds__(256) segbin_kernel(const BwdParams p) {
     make_geo<true>(d, fx, fy, i, j, g);
     ys[0] = ys[1] = g.y0; ys[2] = ys[3] = g.y1;
     xs[0] = xs[2] = g.x0; xs[1] = xs[3] = g.x1;
+    // unclamped corner (-1 and W / H mark out-of-image neighbours; zeros-padding outliers sit at -100)
+    const int ux0 = g.oknw | g.oksw ? g.x0 : (g.okne | g.okse ? g.x1 - 1 : -100);
+    const int uy0 = g.oknw | g.okne ? g.y0 : (g.oksw | g.okse ? g.y1 - 1 : -100);
+    p.pixrec[idx] = make_int4((ux0 & 0xffff) | (uy0 << 16), __float_as_int(g.ax), __float_as_int(g.ay),
+                              __float_as_int(m));
     act[0] = g.oknw && g.wnw * m != 0.f;
     act[1] = g.okne && g.wne * m != 0.f;
     act[2] = g.oksw && g.wsw * m != 0.f;
@@ -464,32 +469,33 @@ __global__ void __launch_bounds__(256, 3) gather_nhwc_kernel(const __grid_consta
       const int si = sr % d.H, sn = sr / d.H;
       const int sj = sbx * TW + lane;
       if (sj < d.W) {
-        const int spix = si * d.W + sj;
-        const float* fl = p.flow + (int64_t)sn * 2 * HW + spix;
-        const float sfx = __ldg(fl), sfy = __ldg(fl + HW);
-        const float sm = HAS_MASK ? __ldg(p.mask + (int64_t)sn * HW + spix) : 1.f;
-        Geo g;
-        make_geo<true>(d, sfx, sfy, si, sj, g);
-        const int ys[4] = {g.y0, g.y0, g.y1, g.y1};
-        const int xs[4] = {g.x0, g.x1, g.x0, g.x1};
-        const float ws[4] = {g.wnw * sm, g.wne * sm, g.wsw * sm, g.wse * sm};
-        const bool oks[4] = {g.oknw, g.okne, g.oksw, g.okse};
-        const int sidx = sn * HW + spix;
+        const int sidx = (sn * d.H + si) * d.W + sj;
+        const int4 rec = __ldg(p.pixrec + sidx);
+        const int ux0 = (int)(short)(rec.x & 0xffff), uy0 = rec.x >> 16;
+        // tile-local position of the nw corner; the four corners are (dy, dx), (dy, dx+1), (dy+1, dx), (dy+1, dx+1)
+        const int dy = uy0 - by * TH, dx = ux0 - bx * TW;
+        if (dy >= -1 && dy < TH && dx >= -1 && dx < TW) {  // at least one corner can fall inside this tile
+          const float ax = __int_as_float(rec.y), ay = __int_as_float(rec.z), sm = __int_as_float(rec.w);
+          // same expressions as make_geo: (x1 - ix) == 1 - ax and (ix - x0) == ax bit for bit
+          const float bxw = 1.f - ax, byw = 1.f - ay;
+          const float ws[4] = {(bxw * byw) * sm, (ax * byw) * sm, (bxw * ay) * sm, (ax * ay) * sm};
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const unsigned dy = (unsigned)(ys[k] - by * TH), dx = (unsigned)(xs[k] - bx * TW);
-          if (oks[k] && ws[k] != 0.f && dy < (unsigned)TH && dx < (unsigned)TW) {
-            const int slot = atomicAdd(&s_cnt[dy][dx], 1);
-            if (slot < CAP) {
-              reinterpret_cast<int2*>(&s_ent[slot >> 1][dy][dx])[slot & 1] =
-                  make_int2((int)((uint32_t)sidx * (uint32_t)C4), __float_as_int(ws[k]));
-            } else {
-              // list full: hand the contribution to overflow_kernel (flag byte per output pixel, shared
-              // with other tiles' overflows of the same pixel -> word-wide atomic OR)
-              unsigned* word = reinterpret_cast<unsigned*>(p.ovf) + (sidx >> 2);
-              const int sh = (sidx & 3) * 8;
-              const unsigned old = atomicOr(word, (1u << k) << sh);
-              if (((old >> sh) & 0xffu) == 0u) p.ovf_list[atomicAdd(p.ovf_count, 1)] = sidx;
+          for (int k = 0; k < 4; ++k) {
+            const int cy = dy + (k >> 1), cx = dx + (k & 1);
+            const int gy = uy0 + (k >> 1), gxx = ux0 + (k & 1);
+            if ((unsigned)cy < (unsigned)TH && (unsigned)cx < (unsigned)TW && gy < d.H && gxx < d.W && ws[k] != 0.f) {
+              const int slot = atomicAdd(&s_cnt[cy][cx], 1);
+              if (slot < CAP) {
+                reinterpret_cast<int2*>(&s_ent[slot >> 1][cy][cx])[slot & 1] =
+                    make_int2((int)((uint32_t)sidx * (uint32_t)C4), __float_as_int(ws[k]));
+              } else {
+                // list full: hand the contribution to overflow_kernel (flag byte per output pixel, shared
+                // with other tiles' overflows of the same pixel -> word-wide atomic OR)
+                unsigned* word = reinterpret_cast<unsigned*>(p.ovf) + (sidx >> 2);
+                const int sh = (sidx & 3) * 8;
+                const unsigned old = atomicOr(word, (1u << k) << sh);
+                if (((old >> sh) & 0xffu) == 0u) p.ovf_list[atomicAdd(p.ovf_count, 1)] = sidx;
+              }
             }
           }
         }
@@ -814,6 +820,7 @@ struct LocalWs {
   unsigned char* ovf;
   int* tlist;
   int* ovf_list;
+  int4* pixrec;
   int cand_cap;
   size_t clear_bytes;
   size_t bytes;
@@ -836,6 +843,8 @@ static LocalWs carve_local(void* base, int64_t N, int H, int W, int64_t x_batch)
   o += up256(ntile * w.cand_cap * sizeof(int));
   w.ovf_list = reinterpret_cast<int*>(b + o);
   o += up256(npix_o * sizeof(int));
+  w.pixrec = reinterpret_cast<int4*>(b + o);
+  o += up256(npix_o * sizeof(int4));
   w.bytes = o;
   return w;
 }
@@ -857,6 +866,7 @@ bool gather_supported(const BwdParams& p, Layout lx, Layout lg) {
     if ((d.C & 3) || ((uintptr_t)p.x & 15) || ((uintptr_t)p.gout & 15) || (p.gx && ((uintptr_t)p.gx & 15)))
       return false;
     if ((int64_t)d.H * d.W * d.C >= (1ll << 30)) return false;  // 32-bit byte offsets inside one image
+    if (d.H >= 32768 || d.W >= 32768) return false;              // 16-bit corner coordinates in the pixel records
     if ((int64_t)d.N * d.H * d.W * (d.C / 4) >= (1ll << 32)) return false;  // 32-bit source keys (16-byte units)
   }
   return true;
@@ -960,6 +970,7 @@ int launch_bwd_gather(const BwdParams& pin, Layout lx, void* workspace, size_t w
     p.tcnt = w.tcnt;
     p.tlist = w.tlist;
     p.cand_cap = w.cand_cap;
+    p.pixrec = w.pixrec;
     p.ovf = w.ovf;
     p.ovf_count = w.ovf_count;
     p.ovf_list = w.ovf_list;
