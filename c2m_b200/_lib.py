@@ -22,6 +22,8 @@ FLAG_NO_FMA = 0x200
 FLAG_FORCE_GENERIC = 0x400
 FLAG_NO_TMA = 0x800
 FLAG_BWD_ATOMIC = 0x1000
+FLAG_STAGE_NHWC = 0x4000
+FLAG_NO_STAGE = 0x8000  # host-side only: keep NCHW tensors on the NCHW kernels (test / tuning hook)
 
 # every symbol include/c2m_warp.h declares (tests/test_abi.py checks the list against the header)
 SYMBOLS = (

@@ -125,6 +125,14 @@ size_t gather_workspace_bytes(int64_t N, int H, int W, int64_t x_batch);
 bool gather_supported(const BwdParams& p, Layout lx, Layout lg);
 int launch_bwd_gather(const BwdParams& pin, Layout lx, void* workspace, size_t workspace_bytes, cudaStream_t st);
 
+static size_t stage_one(int64_t n, int C, int H, int W) {
+  return (((size_t)n * C * H * W * sizeof(float)) + 255) & ~(size_t)255;
+}
+// channels-last staging copies of gout, x and gx
+static size_t stage_bytes(int64_t N, int C, int H, int W, int64_t xb) {
+  return stage_one(N, C, H, W) + 2 * stage_one(xb, C, H, W);
+}
+
 size_t bwd_workspace_bytes(int64_t N, int C, int H, int W, int64_t x_batch, int want_gx, int flags) {
   size_t b = 256;
   if (!want_gx) return b;
@@ -132,9 +140,54 @@ size_t bwd_workspace_bytes(int64_t N, int C, int H, int W, int64_t x_batch, int 
   if (flags & C2M_FLAG_DETERMINISTIC) {
     b += (size_t)xb * C * H * W * sizeof(long long);  // fixed-point accumulator
   } else if (!(flags & (C2M_FLAG_BWD_ATOMIC | C2M_FLAG_FORCE_GENERIC | C2M_FLAG_COORD_GRID))) {
-    b += gather_workspace_bytes(N, H, W, xb);  // contributor lists
+    b += gather_workspace_bytes(N, H, W, xb);  // contributor lists / candidate lists
+    if (flags & C2M_FLAG_STAGE_NHWC) b += stage_bytes(N, C, H, W, xb);
   }
   return b;
+}
+
+// ---------------------------------------------------------------------------------------------
+// NCHW <-> channels-last staging copies ([n][c][hw] <-> [n][hw][c]) through a 32 x 33 shared-memory tile:
+// both sides move 128-byte rows.
+template <bool TO_NHWC>
+__global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int C,
+                                                        int HW) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t img = (int64_t)blockIdx.z * C * HW;
+  const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  if (TO_NHWC) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = c0 + ty + 8 * k, px = p0 + tx;
+      if (c < C && px < HW) tile[ty + 8 * k][tx] = __ldcs(in + img + (int64_t)c * HW + px);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int px = p0 + ty + 8 * k, c = c0 + tx;
+      if (c < C && px < HW) out[img + (int64_t)px * C + c] = tile[tx][ty + 8 * k];
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int px = p0 + ty + 8 * k, c = c0 + tx;
+      if (c < C && px < HW) tile[ty + 8 * k][tx] = __ldcs(in + img + (int64_t)px * C + c);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = c0 + ty + 8 * k, px = p0 + tx;
+      if (c < C && px < HW) __stcs(out + img + (int64_t)c * HW + px, tile[tx][ty + 8 * k]);
+    }
+  }
+}
+
+template <bool TO_NHWC>
+static void launch_transpose(const float* in, float* out, int64_t n, int C, int HW, cudaStream_t st) {
+  const dim3 grid((HW + 31) / 32, (C + 31) / 32, (unsigned)n);
+  transpose_kernel<TO_NHWC><<<grid, 256, 0, st>>>(in, out, C, HW);
+  count_launch();
 }
 
 static int grid_for(int64_t total) {
@@ -143,7 +196,47 @@ static int grid_for(int64_t total) {
   return (int)(blocks > cap ? cap : (blocks < 1 ? 1 : blocks));
 }
 
+// NCHW-dense tensors through the channels-last kernels: gout (and x, when grad-flow / grad-mask are asked for) are
+// copied into channels-last staging buffers, the channels-last backward runs on those, grad-input is copied
+// back.  Three streaming passes over a tensor each way cost less than the scattered 4-byte gathers of the
+// NCHW kernels.
+static int launch_bwd_staged(const BwdParams& pin, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  BwdParams p = pin;
+  const Dims& d = p.d;
+  const int HW = d.H * d.W;
+  char* b = reinterpret_cast<char*>(workspace) + 256;
+  float* gout_t = reinterpret_cast<float*>(b);
+  b += stage_one(d.N, d.C, d.H, d.W);
+  float* x_t = reinterpret_cast<float*>(b);
+  b += stage_one(d.x_batch, d.C, d.H, d.W);
+  float* gx_t = reinterpret_cast<float*>(b);
+  b += stage_one(d.x_batch, d.C, d.H, d.W);
+  const size_t used = (size_t)(b - reinterpret_cast<char*>(workspace));
+  launch_transpose<true>(p.gout, gout_t, d.N, d.C, HW, st);
+  if (p.gflow || p.gmask) launch_transpose<true>(p.x, x_t, d.x_batch, d.C, HW, st);
+  float* gx_out = p.gx;
+  p.gout = gout_t;
+  p.x = x_t;
+  if (p.gx) p.gx = gx_t;
+  const int64_t nhwc[4] = {(int64_t)d.C * HW, 1, (int64_t)d.W * d.C, d.C};
+  for (int k = 0; k < 4; ++k) p.xs[k] = p.gs[k] = nhwc[k];
+  const int rc = launch_bwd_gather(p, LAYOUT_NHWC, b, workspace_bytes - used, st);
+  if (rc) return rc;
+  if (gx_out) launch_transpose<false>(gx_t, gx_out, d.x_batch, d.C, HW, st);
+  return C2M_OK;
+}
+
 int launch_bwd(const BwdParams& pin, Layout lx, Layout lg, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  if ((pin.d.flags & C2M_FLAG_STAGE_NHWC) && lx == LAYOUT_NCHW && lg == LAYOUT_NCHW && workspace &&
+      workspace_bytes >= bwd_workspace_bytes(pin.d.N, pin.d.C, pin.d.H, pin.d.W, pin.d.x_batch, pin.gx != nullptr,
+                                             pin.d.flags) &&
+      pin.gx != nullptr) {
+    // eligibility of the channels-last kernels, judged on the staging buffers (256-byte aligned)
+    BwdParams q = pin;
+    q.x = q.gout = reinterpret_cast<const float*>(workspace);
+    q.gx = reinterpret_cast<float*>(workspace);
+    if (gather_supported(q, LAYOUT_NHWC, LAYOUT_NHWC)) return launch_bwd_staged(pin, workspace, workspace_bytes, st);
+  }
   if (gather_supported(pin, lx, lg))
     return launch_bwd_gather(pin, lx, reinterpret_cast<char*>(workspace) + 256,
                              workspace_bytes >= 256 ? workspace_bytes - 256 : 0, st);

@@ -66,6 +66,9 @@ extern "C" {
 #define C2M_FLAG_FORCE_GENERIC 0x400 /* run the stride-generic kernels (test hook) */
 #define C2M_FLAG_NO_TMA 0x800       /* stage flow/mask with plain loads instead of TMA (test hook) */
 #define C2M_FLAG_BWD_ATOMIC 0x1000  /* bwd: force the direct global-atomics scatter (test hook) */
+#define C2M_FLAG_STAGE_NHWC 0x4000  /* bwd, NCHW-dense tensors: stage gout / x / gx through channels-last copies in the
+                                       workspace and run the channels-last kernels (pass the flag to the workspace
+                                       query too: three tensor-sized staging buffers are added) */
 
 #define C2M_OK 0
 #define C2M_ERR_INVALID 1   /* bad argument (null pointer, size, stride, alignment) */

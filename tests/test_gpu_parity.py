@@ -161,8 +161,9 @@ def test_random_shapes_vs_device_reference(dev, shape, layout):
     assert rel(ours[1][2], torch.from_numpy(r["gmask"])) <= GRAD_TOL
 
 
-@pytest.mark.parametrize("flags", [0, _lib.FLAG_FORCE_GENERIC, _lib.FLAG_NO_TMA, _lib.FLAG_BWD_ATOMIC],
-                         ids=["default", "generic", "no_tma", "bwd_atomic"])
+@pytest.mark.parametrize("flags", [0, _lib.FLAG_FORCE_GENERIC, _lib.FLAG_NO_TMA, _lib.FLAG_BWD_ATOMIC,
+                                   _lib.FLAG_NO_STAGE, _lib.FLAG_NO_STAGE | _lib.FLAG_NO_TMA],
+                         ids=["default", "generic", "no_tma", "bwd_atomic", "no_stage", "no_stage_no_tma"])
 @pytest.mark.parametrize("layout", ["nchw", "nhwc"])
 def test_kernel_variants_agree(dev, flags, layout):
     x, flow, mask, gout = make_inputs(dev, 3, 24, 40, 72, seed=5)
@@ -362,6 +363,9 @@ def test_full_size_properties(dev, cfg):
     out_l, (gx_l, gflow_l, gmask_l) = run_ours(xl, flow, mask, gout)
     assert rel(out_l, out) <= 1e-6
     assert rel(gx_l, gx) <= GRAD_TOL and rel(gflow_l, gflow) <= GRAD_TOL and rel(gmask_l, gmask) <= GRAD_TOL
+    # (6b) NCHW tensors on the NCHW gather kernels (default stages them through channels-last copies)
+    _, (gx_n, gflow_n, gmask_n) = run_ours(x, flow, mask, gout, flags=_lib.FLAG_NO_STAGE)
+    assert rel(gx_n, gx) <= GRAD_TOL and rel(gflow_n, gflow) <= GRAD_TOL and rel(gmask_n, gmask) <= GRAD_TOL
     # (7) deterministic mode: reproducible bits, same values within tolerance
     d1 = run_ours(x, flow, mask, gout, deterministic=True)[1][0]
     d2 = run_ours(x, flow, mask, gout, deterministic=True)[1][0]
