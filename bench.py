@@ -176,6 +176,9 @@ def run_reference(args):
 
 
 def run_ours(args):
+    # rank 0 prints exactly one line on stdout: keep NCCL's version banner off it
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     import c2m_b200
     from c2m_b200 import _lib
     from c2m_b200 import dist as cdist
