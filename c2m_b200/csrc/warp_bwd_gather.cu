@@ -358,15 +358,24 @@ struct DotRegs {
 };
 
 template <int LP, int NQ>
-__device__ __forceinline__ void dot_issue(const char* px, const char* pg, const uint4& off, DotRegs<NQ>& r) {
+__device__ __forceinline__ void dot_issue_x(const char* px, const uint4& off, DotRegs<NQ>& r) {
 #pragma unroll
   for (int q = 0; q < NQ; ++q) {
     r.a[q] = ldg_batch(reinterpret_cast<const float4*>(px + off.x) + q * LP);
     r.b[q] = ldg_batch(reinterpret_cast<const float4*>(px + off.y) + q * LP);
     r.c[q] = ldg_batch(reinterpret_cast<const float4*>(px + off.z) + q * LP);
     r.e[q] = ldg_batch(reinterpret_cast<const float4*>(px + off.w) + q * LP);
-    r.g[q] = ldg_batch(reinterpret_cast<const float4*>(pg) + q * LP);
   }
+}
+template <int LP, int NQ>
+__device__ __forceinline__ void dot_issue_g(const char* pg, DotRegs<NQ>& r) {
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) r.g[q] = ldg_batch(reinterpret_cast<const float4*>(pg) + q * LP);
+}
+template <int LP, int NQ>
+__device__ __forceinline__ void dot_issue(const char* px, const char* pg, const uint4& off, DotRegs<NQ>& r) {
+  dot_issue_x<LP, NQ>(px, off, r);
+  dot_issue_g<LP, NQ>(pg, r);
 }
 
 // sa..se += sum over this lane's channels of gout[c] * x_corner[c]
@@ -580,9 +589,14 @@ __global__ void __launch_bounds__(256, 3) gather_nhwc_kernel(const __grid_consta
           e1 = s_ent[1][warp][pa];
           gx_issue<LP, NQ>(gl, cnt, e0, e1, v);
         }
-        if (DO_GF) dot_issue<LP, NQ>(xl, gol, s_off[warp][pa], dr);
+        if (DO_GF) dot_issue_x<LP, NQ>(xl, s_off[warp][pa], dr);
         if (DO_GX) gx_finish<LP, NQ, NP>(gl, gxl, cnt, e0, e1, &s_ent[0][warp][pa], TH * TW, v);
-        if (DO_GF) dot_finish<NQ>(dr, sa, sb, sc, se);
+        if (DO_GF) {
+          // the pixel's own gout row (an L1 / L2 hit: its neighbours just gathered it) is fetched last, which
+          // keeps the merged batch inside the register budget of three CTAs per SM
+          dot_issue_g<LP, NQ>(gol, dr);
+          dot_finish<NQ>(dr, sa, sb, sc, se);
+        }
       }
     } else if (act) {
 #pragma unroll 1

@@ -1,2 +1,1 @@
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r1p_bench_g2.json 2> gpurun_out/r1p_bench_g2.err
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 2 --warmup 1 > gpurun_out/r1p_bench_ref_g2.json 2> gpurun_out/r1p_bench_ref_g2.err
+timeout 300 bash tools/sweep_env.sh C2M_X 0 > gpurun_out/r1s_sweep.log 2>&1
