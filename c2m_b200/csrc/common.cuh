@@ -82,6 +82,7 @@ struct Geo {
   bool oknw, okne, oksw, okse;
   float gmx, gmy;            // d(clipped coord)/d(flow) = size/2 * clip-grad * inv_b
   float ax, ay;              // ix - x0, iy - y0 (for the coordinate gradient)
+  bool clipx, clipy;         // border padding: coordinate was clipped (its gradient w.r.t. the flow is zero)
 };
 
 __device__ __forceinline__ float base_coord(int k, int n, float step) {
@@ -154,6 +155,8 @@ __device__ __forceinline__ void make_geo(const Dims& d, float fx, float fy, int 
   // ATen: grad_grid = (size/2 * clip_grad) * gix; autograd of ops.py:190 multiplies by 1/((size-1)/2)
   g.gmx = cgx * (0.5f * (float)d.W) * sx;
   g.gmy = cgy * (0.5f * (float)d.H) * sy;
+  g.clipx = cgx == 0.f;
+  g.clipy = cgy == 0.f;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -313,8 +313,9 @@ __device__ __forceinline__ void gx_issue(const char* gl, int cnt, const int4& e0
 template <int LP, int NQ, int NP>
 __device__ __forceinline__ void gx_finish(const char* gl, char* po, int cnt, const int4& e0, const int4& e1,
                                           const int4* ent, int pstride, const float4 (&v)[4][NQ]) {
-  const float w0 = __int_as_float(e0.y), w1 = __int_as_float(e0.w);
-  const float w2 = __int_as_float(e1.y), w3 = __int_as_float(e1.w);
+  // slots past the count may hold anything (their loads were predicated off and read as zero): weight 0
+  const float w0 = cnt > 0 ? __int_as_float(e0.y) : 0.f, w1 = cnt > 1 ? __int_as_float(e0.w) : 0.f;
+  const float w2 = cnt > 2 ? __int_as_float(e1.y) : 0.f, w3 = cnt > 3 ? __int_as_float(e1.w) : 0.f;
   float4 acc[NQ];
 #pragma unroll
   for (int q = 0; q < NQ; ++q) {
@@ -407,9 +408,9 @@ __global__ void __launch_bounds__(256, 3) gather_nhwc_kernel(const __grid_consta
   __shared__ alignas(128) float s_mask[TH][TW];
   __shared__ alignas(8) uint64_t bar;
   __shared__ uint4 s_off[DO_GF ? TH : 1][TW];   // byte offsets of the four corners inside the image
-  __shared__ float4 s_w[DO_GF ? TH : 1][TW];    // bilinear weights
-  __shared__ float4 s_aux[DO_GF ? TH : 1][TW];  // ax, ay, gmx, gmy; later the pixel's (gflow_x, gflow_y, gmask)
-  __shared__ float2 s_mk[DO_GF ? TH : 1][TW];   // mask value, in-bounds bits
+  // ax, ay, mask, flags (bits 0-3: corner inside the image, 4 / 5: x / y coordinate clipped -> zero
+  // grad-flow); later the pixel's (gflow_x, gflow_y, gmask)
+  __shared__ float4 s_aux[DO_GF ? TH : 1][TW];
   __shared__ int s_cnt[DO_GX ? TH : 1][TW];
   __shared__ int4 s_ent[DO_GX ? NP : 1][DO_GX ? TH : 1][TW];
   const Dims& d = p.d;
@@ -515,16 +516,8 @@ __global__ void __launch_bounds__(256, 3) gather_nhwc_kernel(const __grid_consta
   if (DO_GX && live) {
     const int self = (int)(((uint32_t)n * (uint32_t)HW + (uint32_t)pix) * (uint32_t)C4);  // a valid gout pixel for padding
     if (LOCAL) {
-      // clamp the count, pad the first four slots with (own pixel, weight 0): phase 1 then needs no branch there
-      const int c = min(s_cnt[warp][lane], CAP);
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        int4 e = s_ent[k][warp][lane];
-        if (2 * k >= c) { e.x = self; e.y = 0; }
-        if (2 * k + 1 >= c) { e.z = self; e.w = 0; }
-        s_ent[k][warp][lane] = e;
-      }
-      s_cnt[warp][lane] = c;
+      // nothing to stage: the lists are already in shared memory (phase 1 clamps the count and ignores
+      // the slots past it)
     } else {  // global lists (issued before the TMA wait so the two overlap)
       const int64_t ndest = (int64_t)HW * d.x_batch;
       const int64_t D = (int64_t)n * HW + pix;
@@ -556,10 +549,9 @@ __global__ void __launch_bounds__(256, 3) gather_nhwc_kernel(const __grid_consta
     make_geo<true>(d, fx, fy, i, min(j, d.W - 1), g);
     s_off[warp][lane] = make_uint4((uint32_t)(g.y0 * d.W + g.x0) * pxb, (uint32_t)(g.y0 * d.W + g.x1) * pxb,
                                    (uint32_t)(g.y1 * d.W + g.x0) * pxb, (uint32_t)(g.y1 * d.W + g.x1) * pxb);
-    s_w[warp][lane] = make_float4(g.wnw, g.wne, g.wsw, g.wse);
-    s_aux[warp][lane] = make_float4(g.ax, g.ay, g.gmx, g.gmy);
-    const int ok = (int)g.oknw | ((int)g.okne << 1) | ((int)g.oksw << 2) | ((int)g.okse << 3);
-    s_mk[warp][lane] = make_float2(m, __int_as_float(ok));
+    const int ok = (int)g.oknw | ((int)g.okne << 1) | ((int)g.oksw << 2) | ((int)g.okse << 3) |
+                   ((int)g.clipx << 4) | ((int)g.clipy << 5);
+    s_aux[warp][lane] = make_float4(g.ax, g.ay, m, __int_as_float(ok));
   }
   __syncwarp();
   const int lq = lane % LP, grp = lane / LP;
@@ -584,7 +576,7 @@ __global__ void __launch_bounds__(256, 3) gather_nhwc_kernel(const __grid_consta
       DotRegs<NQ> dr;
       if (act) {
         if (DO_GX) {
-          cnt = s_cnt[warp][pa];
+          cnt = min(s_cnt[warp][pa], CAP);
           e0 = s_ent[0][warp][pa];
           e1 = s_ent[1][warp][pa];
           gx_issue<LP, NQ>(gl, cnt, e0, e1, v);
@@ -602,7 +594,7 @@ __global__ void __launch_bounds__(256, 3) gather_nhwc_kernel(const __grid_consta
 #pragma unroll 1
       for (int qi = 0; qi < nq; ++qi) {
         if (DO_GX) {
-          const int cnt = s_cnt[warp][pa];
+          const int cnt = min(s_cnt[warp][pa], CAP);
           const int4 e0 = s_ent[0][warp][pa], e1 = s_ent[1][warp][pa];
           float4 v[4][1];
           gx_issue<LP, 1>(gl + qi * (LP * 16), cnt, e0, e1, v);
@@ -617,17 +609,17 @@ __global__ void __launch_bounds__(256, 3) gather_nhwc_kernel(const __grid_consta
     }
     if (DO_GF) {
       const int pr = act ? pa : 0;
-      const float2 mk = s_mk[warp][pr];
-      const int ok = __float_as_int(mk.y);
+      const float4 aux = s_aux[warp][pr];  // ax, ay, mask, flags
+      const int ok = __float_as_int(aux.w);
       if (!(ok & 1)) sa = 0.f;  // corners outside the image contribute nothing (ATen within_bounds)
       if (!(ok & 2)) sb = 0.f;
       if (!(ok & 4)) sc = 0.f;
       if (!(ok & 8)) se = 0.f;
-      const float4 w = s_w[warp][pr];
-      const float4 aux = s_aux[warp][pr];  // ax, ay, gmx, gmy
-      float gix = (sb - sa) * (1.f - aux.y) + (se - sc) * aux.y;
-      float giy = (sc - sa) * (1.f - aux.x) + (se - sb) * aux.x;
-      float gm = fmaf(se, w.w, fmaf(sc, w.z, fmaf(sb, w.y, sa * w.x)));
+      // bilinear weights from the fractions: x1 - ix == 1 - ax and ix - x0 == ax, the expressions of make_geo
+      const float bxw = 1.f - aux.x, byw = 1.f - aux.y;
+      float gix = (sb - sa) * byw + (se - sc) * aux.y;
+      float giy = (sc - sa) * bxw + (se - sb) * aux.x;
+      float gm = fmaf(se, aux.x * aux.y, fmaf(sc, bxw * aux.y, fmaf(sb, aux.x * byw, sa * (bxw * byw))));
 #pragma unroll
       for (int o = LP >> 1; o > 0; o >>= 1) {
         gix += __shfl_xor_sync(0xffffffffu, gix, o);
@@ -636,8 +628,11 @@ __global__ void __launch_bounds__(256, 3) gather_nhwc_kernel(const __grid_consta
       }
       // (the shuffles above are the convergence point between the group's reads of slot `pa` and this write)
       if (lq == 0 && act) {
-        const float mm = HAS_MASK ? mk.x : 1.f;  // the sums used gout, not gout*mask
-        s_aux[warp][pa] = make_float4(gix * mm * aux.z, giy * mm * aux.w, gm, 0.f);
+        const float mm = HAS_MASK ? aux.z : 1.f;  // the sums used gout, not gout*mask
+        // d(clipped coordinate)/d(flow), as make_geo forms it: clip-grad * size/2 * 1/((size-1)/2)
+        const float gmx = ((ok & 16) ? 0.f : 1.f) * (0.5f * (float)d.W) * d.inv_bw;
+        const float gmy = ((ok & 32) ? 0.f : 1.f) * (0.5f * (float)d.H) * d.inv_bh;
+        s_aux[warp][pa] = make_float4(gix * mm * gmx, giy * mm * gmy, gm, 0.f);
       }
     }
     if (DO_GX) gxl += G * pxb;
