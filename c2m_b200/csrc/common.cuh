@@ -56,8 +56,9 @@ struct BwdParams {
   int cchunk;
   // deterministic mode
   long long* acc64;         // fixed-point accumulator, same element order as gx
-  const unsigned* maxbits;  // bit pattern of max|gout*mask|
+  const unsigned* maxbits;  // bit pattern of max|gout*mask| (channels-last gather: [0] max|gout|, [1] max|mask|)
   int count_log2;           // ceil(log2(max contributions per destination))
+  unsigned char* touched;   // deterministic channels-last gather: [x_batch*H*W] destination has terms in acc64
   // gather-form backward (contributor lists built by bin_kernel)
   int* cnt;                 // [x_batch*H*W] contributions seen per destination pixel
   void* entries;            // [x_batch*H*W][kListCap] ListEntry
@@ -158,6 +159,19 @@ __device__ __forceinline__ void make_geo(const Dims& d, float fx, float fy, int 
   g.clipx = cgx == 0.f;
   g.clipy = cgy == 0.f;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Deterministic grad-input: every term w * gout is converted to 64-bit fixed point with a power-of-two
+// scale and summed as an integer -- the result does not depend on the order (or on which mechanism adds
+// which term) and is converted back to float once.  scale = 2^(60 - count_log2 - exponent(max |term|)).
+__device__ __forceinline__ float fixed_scale_from(float mx, int count_log2) {
+  int e = 0;
+  if (mx > 0.f && mx < 3.0e38f) frexpf(mx, &e);
+  int k = 60 - count_log2 - e;
+  k = max(-120, min(120, k));
+  return exp2f((float)k);
+}
+__device__ __forceinline__ long long to_fixed(float term, float scale) { return __float2ll_rn(term * scale); }
 
 // ---------------------------------------------------------------------------------------------
 // mbarrier + TMA (cp.async.bulk.tensor) wrappers

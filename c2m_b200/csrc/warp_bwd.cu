@@ -122,6 +122,7 @@ __global__ void __launch_bounds__(256) fix2float_kernel(const long long* acc, fl
 
 // ---------------------------------------------------------------------------------------------
 size_t gather_workspace_bytes(int64_t N, int H, int W, int64_t x_batch);
+size_t local_det_workspace_bytes(int64_t N, int C, int H, int W, int64_t x_batch);
 bool gather_supported(const BwdParams& p, Layout lx, Layout lg);
 int launch_bwd_gather(const BwdParams& pin, Layout lx, void* workspace, size_t workspace_bytes, cudaStream_t st);
 
@@ -138,7 +139,11 @@ size_t bwd_workspace_bytes(int64_t N, int C, int H, int W, int64_t x_batch, int 
   if (!want_gx) return b;
   const int64_t xb = x_batch > 0 ? x_batch : N;
   if (flags & C2M_FLAG_DETERMINISTIC) {
-    b += (size_t)xb * C * H * W * sizeof(long long);  // fixed-point accumulator
+    // the larger of the two deterministic schemes (the caller does not tell the layout): the fixed-point
+    // scatter of the generic kernels, or the channels-last gather with its fixed-point overflow rows
+    const size_t a = (size_t)xb * C * H * W * sizeof(long long), l = local_det_workspace_bytes(N, C, H, W, xb);
+    b += a > l ? a : l;
+    if (flags & C2M_FLAG_STAGE_NHWC) b += stage_bytes(N, C, H, W, xb);
   } else if (!(flags & (C2M_FLAG_BWD_ATOMIC | C2M_FLAG_FORCE_GENERIC | C2M_FLAG_COORD_GRID))) {
     b += gather_workspace_bytes(N, H, W, xb);  // contributor lists / candidate lists
     if (flags & C2M_FLAG_STAGE_NHWC) b += stage_bytes(N, C, H, W, xb);

@@ -210,7 +210,9 @@ struct OvfRec {
   float v[4];    // weight * mask, 0 for corners that did fit their list
 };
 
-template <bool VEC4>
+// DET: the terms go to the 64-bit fixed-point accumulator instead (deterministic channels-last gather; runs
+// BEFORE the gather, which folds the accumulator rows of the marked destinations into its own sums).
+template <bool VEC4, bool DET = false>
 __global__ void __launch_bounds__(256) overflow_kernel(const BwdParams p) {
   constexpr int GS = VEC4 ? 16 : 32;
   constexpr int NG = 256 / GS;
@@ -250,7 +252,23 @@ __global__ void __launch_bounds__(256) overflow_kernel(const BwdParams p) {
 #pragma unroll 2
     for (int k = grp; k < nrec; k += NG) {
       const OvfRec& rec = s_rec[k];
-      if (VEC4) {
+      if (DET) {
+        const float scale = fixed_scale_from(__uint_as_float(p.maxbits[0]) * __uint_as_float(p.maxbits[1]), p.count_log2);
+        for (int c = gl; c < d.C; c += GS) {
+          const float go = p.gout[rec.g0 + c];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float v = rec.v[q];
+            if (v != 0.f)
+              atomicAdd(reinterpret_cast<unsigned long long*>(p.acc64 + rec.a[q] + c), (unsigned long long)to_fixed(v * go, scale));
+          }
+        }
+        if (gl == 0) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (rec.v[q] != 0.f) p.touched[rec.a[q] / d.C] = 1;
+        }
+      } else if (VEC4) {
         for (int c = gl * 4; c < d.C; c += GS * 4) {
           const float4 go = ldg_batch(reinterpret_cast<const float4*>(p.gout + rec.g0 + c));
           float* gx = p.gx + c;
@@ -353,6 +371,68 @@ __device__ __forceinline__ void gx_finish(const char* gl, char* po, int cnt, con
   for (int q = 0; q < NQ; ++q) st_stream(reinterpret_cast<float4*>(po) + q * LP, acc[q]);
 }
 
+// Deterministic flavour of gx_finish: integer accumulation (see fixed_scale_from); `hot` destinations
+// also have terms in the global accumulator (list overflow, incoherent segments), added before the one
+// conversion back to float.
+template <int LP, int NQ, int NP>
+__device__ __forceinline__ void gx_finish_det(const char* gl, char* po, int cnt, const int4& e0, const int4& e1,
+                                              const int4* ent, int pstride, const float4 (&v)[4][NQ], float scale,
+                                              float inv_scale, const long long* hot_acc) {
+  long long acc[NQ][4];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0;
+  const float w[4] = {__int_as_float(e0.y), __int_as_float(e0.w), __int_as_float(e1.y), __int_as_float(e1.w)};
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (cnt > k) {
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        acc[q][0] += to_fixed(w[k] * v[k][q].x, scale);
+        acc[q][1] += to_fixed(w[k] * v[k][q].y, scale);
+        acc[q][2] += to_fixed(w[k] * v[k][q].z, scale);
+        acc[q][3] += to_fixed(w[k] * v[k][q].w, scale);
+      }
+    }
+  if (cnt > 4) {
+#pragma unroll
+    for (int k = 2; k < NP; ++k) {
+      if (cnt > 2 * k) {
+        const int4 e = ent[k * pstride];
+        const float4* b0 = key_ptr(gl, e.x);
+        const float4* b1 = key_ptr(gl, e.z);
+        const bool two = cnt > 2 * k + 1;
+        float4 u[2][NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          u[0][q] = ldg_batch(b0 + q * LP);
+          u[1][q] = ldg_batch_if(b1 + q * LP, two);
+        }
+        const float wa = __int_as_float(e.y), wb = two ? __int_as_float(e.w) : 0.f;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          acc[q][0] += to_fixed(wa * u[0][q].x, scale) + to_fixed(wb * u[1][q].x, scale);
+          acc[q][1] += to_fixed(wa * u[0][q].y, scale) + to_fixed(wb * u[1][q].y, scale);
+          acc[q][2] += to_fixed(wa * u[0][q].z, scale) + to_fixed(wb * u[1][q].z, scale);
+          acc[q][3] += to_fixed(wa * u[0][q].w, scale) + to_fixed(wb * u[1][q].w, scale);
+        }
+      }
+    }
+  }
+  if (hot_acc) {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const longlong2 h0 = __ldcg(reinterpret_cast<const longlong2*>(hot_acc + q * LP * 4));
+      const longlong2 h1 = __ldcg(reinterpret_cast<const longlong2*>(hot_acc + q * LP * 4 + 2));
+      acc[q][0] += h0.x; acc[q][1] += h0.y; acc[q][2] += h1.x; acc[q][3] += h1.y;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < NQ; ++q)
+    st_stream(reinterpret_cast<float4*>(po) + q * LP,
+              make_float4(__ll2float_rn(acc[q][0]) * inv_scale, __ll2float_rn(acc[q][1]) * inv_scale,
+                          __ll2float_rn(acc[q][2]) * inv_scale, __ll2float_rn(acc[q][3]) * inv_scale));
+}
+
 template <int NQ>
 struct DotRegs {
   float4 a[NQ], b[NQ], c[NQ], e[NQ], g[NQ];
@@ -396,7 +476,8 @@ __device__ __forceinline__ void dot_finish(const DotRegs<NQ>& r, float& sa, floa
 //   LOCAL   the contributor lists are built by the CTA itself in shared memory from the row segments that
 //           segbin_kernel registered as candidates for this destination tile (no global lists, no global
 //           atomics per contribution); otherwise they are read from the global lists bin_kernel wrote.
-template <int LP, int QI, bool DO_GX, bool DO_GF, bool HAS_MASK, bool USE_TMA, bool LOCAL>
+//   DET     deterministic grad-input (local binning only): fixed-point integer accumulation
+template <int LP, int QI, bool DO_GX, bool DO_GF, bool HAS_MASK, bool USE_TMA, bool LOCAL, bool DET = false>
 __global__ void __launch_bounds__(256, 3) gather_nhwc_kernel(const __grid_constant__ BwdParams p,
                                                              const __grid_constant__ CUtensorMap tm_flow,
                                                              const __grid_constant__ CUtensorMap tm_mask) {
@@ -471,6 +552,8 @@ __global__ void __launch_bounds__(256, 3) gather_nhwc_kernel(const __grid_consta
     const int* tl = p.tlist + (int64_t)T * p.cand_cap;
     const int myid = (warp + 8 * lane < ncand) ? __ldg(tl + warp + 8 * lane) : 0;  // warp w takes c = w, w+8, ...
     const int nit = (ncand - warp + 7) >> 3;
+    const float det_scale = DET ? fixed_scale_from(__uint_as_float(p.maxbits[0]) * __uint_as_float(p.maxbits[1]),
+                                                   p.count_log2) : 1.f;
 #pragma unroll 2
     for (int it = 0; it < nit; ++it) {
       const int seg = __shfl_sync(0xffffffffu, myid, it);
@@ -478,6 +561,10 @@ __global__ void __launch_bounds__(256, 3) gather_nhwc_kernel(const __grid_consta
       const int sr = seg / tiles_x;
       const int si = sr % d.H, sn = sr / d.H;
       const int sj = sbx * TW + lane;
+      // deterministic mode: contributions that found their list full (bit k), kept for the warp-wide push below
+      unsigned failbits = 0;
+      int f_pos = 0, f_sidx = 0;
+      float f_ax = 0.f, f_ay = 0.f, f_m = 0.f;
       if (sj < d.W) {
         const int sidx = (sn * d.H + si) * d.W + sj;
         const int4 rec = __ldg(p.pixrec + sidx);
@@ -498,6 +585,9 @@ __global__ void __launch_bounds__(256, 3) gather_nhwc_kernel(const __grid_consta
               if (slot < CAP) {
                 reinterpret_cast<int2*>(&s_ent[slot >> 1][cy][cx])[slot & 1] =
                     make_int2((int)((uint32_t)sidx * (uint32_t)C4), __float_as_int(ws[k]));
+              } else if (DET) {
+                failbits |= 1u << k;
+                f_pos = rec.x; f_sidx = sidx; f_ax = ax; f_ay = ay; f_m = sm;
               } else {
                 // list full: hand the contribution to overflow_kernel (flag byte per output pixel, shared
                 // with other tiles' overflows of the same pixel -> word-wide atomic OR)
@@ -510,7 +600,35 @@ __global__ void __launch_bounds__(256, 3) gather_nhwc_kernel(const __grid_consta
           }
         }
       }
+      if (DET) {
+        // list overflow in deterministic mode: the whole warp adds the term to the destination's global
+        // fixed-point row (lanes across channels) and marks the destination; phase 1 of this same CTA
+        // picks the row up before it converts
+        unsigned any = __ballot_sync(0xffffffffu, failbits != 0u);
+        while (any) {
+          const int src = __ffs(any) - 1;
+          any &= any - 1;
+          const unsigned fb = __shfl_sync(0xffffffffu, failbits, src);
+          const int pos = __shfl_sync(0xffffffffu, f_pos, src), sx = __shfl_sync(0xffffffffu, f_sidx, src);
+          const float ax = __shfl_sync(0xffffffffu, f_ax, src), ay = __shfl_sync(0xffffffffu, f_ay, src);
+          const float sm = __shfl_sync(0xffffffffu, f_m, src);
+          const int ux0 = (int)(short)(pos & 0xffff), uy0 = pos >> 16;
+          const float bxw = 1.f - ax, byw = 1.f - ay;
+          const float ws[4] = {(bxw * byw) * sm, (ax * byw) * sm, (bxw * ay) * sm, (ax * ay) * sm};
+          const float* gsrc = p.gout + (int64_t)sx * d.C;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (fb & (1u << k)) {
+              const int64_t D = (int64_t)n * HW + (int64_t)(uy0 + (k >> 1)) * d.W + (ux0 + (k & 1));
+              for (int c = lane; c < d.C; c += 32)
+                atomicAdd(reinterpret_cast<unsigned long long*>(p.acc64 + D * d.C + c),
+                          (unsigned long long)to_fixed(ws[k] * __ldg(gsrc + c), det_scale));
+              if (lane == 0) p.touched[D] = 1;
+            }
+        }
+      }
     }
+    if (DET) __threadfence();
     __syncthreads();
   }
   if (DO_GX && live) {
@@ -518,6 +636,7 @@ __global__ void __launch_bounds__(256, 3) gather_nhwc_kernel(const __grid_consta
     if (LOCAL) {
       // nothing to stage: the lists are already in shared memory (phase 1 clamps the count and ignores
       // the slots past it)
+      if (DET && __ldcg(p.touched + (int64_t)n * HW + pix)) s_cnt[warp][lane] |= 0x40000000;
     } else {  // global lists (issued before the TMA wait so the two overlap)
       const int64_t ndest = (int64_t)HW * d.x_batch;
       const int64_t D = (int64_t)n * HW + pix;
@@ -557,6 +676,9 @@ __global__ void __launch_bounds__(256, 3) gather_nhwc_kernel(const __grid_consta
   const int lq = lane % LP, grp = lane / LP;
   const int npx = min(TW, d.W - bx * TW);
   const int nq = QI > 0 ? QI : (C4 - lq + LP - 1) / LP;
+  const float det_scale_m = (DET && DO_GX) ? fixed_scale_from(__uint_as_float(p.maxbits[0]) * __uint_as_float(p.maxbits[1]),
+                                                              p.count_log2) : 1.f;
+  const float det_inv_m = 1.f / det_scale_m;  // a power of two: exact
   const char* gl = reinterpret_cast<const char*>(p.gout) + lq * 16;  // + 16 * source key
   const char* xl = reinterpret_cast<const char*>(p.x) + (int64_t)(n % d.x_batch) * HW * pxb + lq * 16;
   const int64_t rowpix = (int64_t)n * HW + (int64_t)i * d.W + bx * TW + grp;  // this lane group's first pixel
@@ -576,13 +698,20 @@ __global__ void __launch_bounds__(256, 3) gather_nhwc_kernel(const __grid_consta
       DotRegs<NQ> dr;
       if (act) {
         if (DO_GX) {
-          cnt = min(s_cnt[warp][pa], CAP);
+          cnt = min(s_cnt[warp][pa] & 0xffffff, CAP);
           e0 = s_ent[0][warp][pa];
           e1 = s_ent[1][warp][pa];
           gx_issue<LP, NQ>(gl, cnt, e0, e1, v);
         }
         if (DO_GF) dot_issue_x<LP, NQ>(xl, s_off[warp][pa], dr);
-        if (DO_GX) gx_finish<LP, NQ, NP>(gl, gxl, cnt, e0, e1, &s_ent[0][warp][pa], TH * TW, v);
+        if (DO_GX && DET) {
+          const bool hot = (s_cnt[warp][pa] & 0x40000000) != 0;
+          const long long* ha = p.acc64 + (rowpix + s) * (int64_t)d.C + lq * 4;
+          gx_finish_det<LP, NQ, NP>(gl, gxl, cnt, e0, e1, &s_ent[0][warp][pa], TH * TW, v, det_scale_m, det_inv_m,
+                                    hot ? ha : nullptr);
+        } else if (DO_GX) {
+          gx_finish<LP, NQ, NP>(gl, gxl, cnt, e0, e1, &s_ent[0][warp][pa], TH * TW, v);
+        }
         if (DO_GF) {
           // the pixel's own gout row (an L1 / L2 hit: its neighbours just gathered it) is fetched last, which
           // keeps the merged batch inside the register budget of three CTAs per SM
@@ -594,11 +723,18 @@ __global__ void __launch_bounds__(256, 3) gather_nhwc_kernel(const __grid_consta
 #pragma unroll 1
       for (int qi = 0; qi < nq; ++qi) {
         if (DO_GX) {
-          const int cnt = min(s_cnt[warp][pa], CAP);
+          const int cnt = min(s_cnt[warp][pa] & 0xffffff, CAP);
           const int4 e0 = s_ent[0][warp][pa], e1 = s_ent[1][warp][pa];
           float4 v[4][1];
           gx_issue<LP, 1>(gl + qi * (LP * 16), cnt, e0, e1, v);
-          gx_finish<LP, 1, NP>(gl + qi * (LP * 16), gxl + qi * (LP * 16), cnt, e0, e1, &s_ent[0][warp][pa], TH * TW, v);
+          if (DET) {
+            const bool hot = (s_cnt[warp][pa] & 0x40000000) != 0;
+            const long long* ha = p.acc64 + (rowpix + s) * (int64_t)d.C + (lq + qi * LP) * 4;
+            gx_finish_det<LP, 1, NP>(gl + qi * (LP * 16), gxl + qi * (LP * 16), cnt, e0, e1, &s_ent[0][warp][pa],
+                                     TH * TW, v, det_scale_m, det_inv_m, hot ? ha : nullptr);
+          } else {
+            gx_finish<LP, 1, NP>(gl + qi * (LP * 16), gxl + qi * (LP * 16), cnt, e0, e1, &s_ent[0][warp][pa], TH * TW, v);
+          }
         }
         if (DO_GF) {
           DotRegs<1> dr;
@@ -833,9 +969,14 @@ struct LocalWs {
   int cand_cap;
   size_t clear_bytes;
   size_t bytes;
+  // deterministic mode only
+  unsigned* maxbits;
+  unsigned char* touched;
+  long long* acc64;
+  size_t det_clear_bytes;  // [maxbits | touched | acc64]
 };
 
-static LocalWs carve_local(void* base, int64_t N, int H, int W, int64_t x_batch) {
+static LocalWs carve_local(void* base, int64_t N, int H, int W, int64_t x_batch, int C = 0, bool det = false) {
   const size_t ntile = (size_t)x_batch * ((H + 7) / 8) * ((W + 31) / 32), npix_o = (size_t)N * H * W;
   LocalWs w;
   int64_t cap = (int64_t)kCandPerFrame * (x_batch > 0 ? N / x_batch : 1);
@@ -854,8 +995,26 @@ static LocalWs carve_local(void* base, int64_t N, int H, int W, int64_t x_batch)
   o += up256(npix_o * sizeof(int));
   w.pixrec = reinterpret_cast<int4*>(b + o);
   o += up256(npix_o * sizeof(int4));
+  w.maxbits = nullptr;
+  w.touched = nullptr;
+  w.acc64 = nullptr;
+  w.det_clear_bytes = 0;
+  if (det) {
+    const size_t npix_d = (size_t)x_batch * H * W, o0 = o;
+    w.maxbits = reinterpret_cast<unsigned*>(b + o);
+    o += 256;
+    w.touched = reinterpret_cast<unsigned char*>(b + o);
+    o += up256(npix_d);
+    w.acc64 = reinterpret_cast<long long*>(b + o);
+    o += up256(npix_d * (size_t)C * sizeof(long long));
+    w.det_clear_bytes = o - o0;
+  }
   w.bytes = o;
   return w;
+}
+
+size_t local_det_workspace_bytes(int64_t N, int C, int H, int W, int64_t x_batch) {
+  return carve_local(nullptr, N, H, W, x_batch, C, true).bytes;
 }
 
 // the caller does not tell the layout when it asks: size for the larger (global-list) scheme
@@ -864,10 +1023,13 @@ size_t gather_workspace_bytes(int64_t N, int H, int W, int64_t x_batch) {
   return a > b ? a : b;
 }
 
+static bool use_local_binning();
+
 bool gather_supported(const BwdParams& p, Layout lx, Layout lg) {
   const Dims& d = p.d;
-  if (d.flags & (C2M_FLAG_DETERMINISTIC | C2M_FLAG_BWD_ATOMIC | C2M_FLAG_FORCE_GENERIC | C2M_FLAG_COORD_GRID))
-    return false;
+  if (d.flags & (C2M_FLAG_BWD_ATOMIC | C2M_FLAG_FORCE_GENERIC | C2M_FLAG_COORD_GRID)) return false;
+  // deterministic grad-input: only the channels-last local-binning gather has an order-independent form
+  if ((d.flags & C2M_FLAG_DETERMINISTIC) && p.gx && !(lx == LAYOUT_NHWC && use_local_binning())) return false;
   if (p.other || p.gother) return false;
   if (lx != lg || lx == LAYOUT_OTHER) return false;
   if ((int64_t)d.N * d.H * d.W >= (1ll << 31) - 1) return false;
@@ -881,7 +1043,7 @@ bool gather_supported(const BwdParams& p, Layout lx, Layout lg) {
   return true;
 }
 
-template <int LP, int QI, bool DO_GX, bool DO_GF, bool LOCAL>
+template <int LP, int QI, bool DO_GX, bool DO_GF, bool LOCAL, bool DET>
 static void launch_gather_nhwc(BwdParams p, cudaStream_t st) {
   p.pf_tiles = prefetch_tiles(0);  // measured: own tile, issued at CTA start, is the best distance
   constexpr int TH = 8, TW = 32;
@@ -891,7 +1053,7 @@ static void launch_gather_nhwc(BwdParams p, cudaStream_t st) {
   memset(&tm, 0, sizeof(tm));
   if (DO_GF) tm = make_tile_maps(d, p.flow, p.mask, TH, TW);
 #define C2M_LAUNCH(MASK, TMA) \
-  gather_nhwc_kernel<LP, QI, DO_GX, DO_GF, MASK, TMA, LOCAL><<<tiles, TH * TW, 0, st>>>(p, tm.flow, tm.mask)
+  gather_nhwc_kernel<LP, QI, DO_GX, DO_GF, MASK, TMA, LOCAL, DET><<<tiles, TH * TW, 0, st>>>(p, tm.flow, tm.mask)
   if (p.mask) {
     if (tm.ok) C2M_LAUNCH(true, true); else C2M_LAUNCH(true, false);
   } else {
@@ -901,23 +1063,23 @@ static void launch_gather_nhwc(BwdParams p, cudaStream_t st) {
   count_launch();
 }
 
-template <bool DO_GX, bool DO_GF, bool LOCAL>
+template <bool DO_GX, bool DO_GF, bool LOCAL, bool DET = false>
 static void launch_gather_nhwc_lp(const BwdParams& p, cudaStream_t st) {
   const int C4 = p.d.C / 4;
   switch (C4) {  // two float4 groups per lane where C allows: half the per-pixel overhead of one
-    case 1: return launch_gather_nhwc<1, 1, DO_GX, DO_GF, LOCAL>(p, st);
-    case 2: return launch_gather_nhwc<1, 2, DO_GX, DO_GF, LOCAL>(p, st);
-    case 4: return launch_gather_nhwc<2, 2, DO_GX, DO_GF, LOCAL>(p, st);
-    case 8: return launch_gather_nhwc<4, 2, DO_GX, DO_GF, LOCAL>(p, st);
-    case 16: return launch_gather_nhwc<8, 2, DO_GX, DO_GF, LOCAL>(p, st);
-    case 32: return launch_gather_nhwc<16, 2, DO_GX, DO_GF, LOCAL>(p, st);
-    case 64: return launch_gather_nhwc<32, 2, DO_GX, DO_GF, LOCAL>(p, st);
+    case 1: return launch_gather_nhwc<1, 1, DO_GX, DO_GF, LOCAL, DET>(p, st);
+    case 2: return launch_gather_nhwc<1, 2, DO_GX, DO_GF, LOCAL, DET>(p, st);
+    case 4: return launch_gather_nhwc<2, 2, DO_GX, DO_GF, LOCAL, DET>(p, st);
+    case 8: return launch_gather_nhwc<4, 2, DO_GX, DO_GF, LOCAL, DET>(p, st);
+    case 16: return launch_gather_nhwc<8, 2, DO_GX, DO_GF, LOCAL, DET>(p, st);
+    case 32: return launch_gather_nhwc<16, 2, DO_GX, DO_GF, LOCAL, DET>(p, st);
+    case 64: return launch_gather_nhwc<32, 2, DO_GX, DO_GF, LOCAL, DET>(p, st);
     default: break;
   }
-  if (C4 >= 24) return launch_gather_nhwc<32, 0, DO_GX, DO_GF, LOCAL>(p, st);
-  if (C4 >= 12) return launch_gather_nhwc<16, 0, DO_GX, DO_GF, LOCAL>(p, st);
-  if (C4 >= 6) return launch_gather_nhwc<8, 0, DO_GX, DO_GF, LOCAL>(p, st);
-  return launch_gather_nhwc<4, 0, DO_GX, DO_GF, LOCAL>(p, st);
+  if (C4 >= 24) return launch_gather_nhwc<32, 0, DO_GX, DO_GF, LOCAL, DET>(p, st);
+  if (C4 >= 12) return launch_gather_nhwc<16, 0, DO_GX, DO_GF, LOCAL, DET>(p, st);
+  if (C4 >= 6) return launch_gather_nhwc<8, 0, DO_GX, DO_GF, LOCAL, DET>(p, st);
+  return launch_gather_nhwc<4, 0, DO_GX, DO_GF, LOCAL, DET>(p, st);
 }
 
 template <bool DO_GX, bool DO_GF, bool REPEAT>
@@ -952,6 +1114,26 @@ static void launch_gather_nchw(BwdParams p, cudaStream_t st) {
   count_launch();
 }
 
+// max |a[i]| over a dense array, as the bit pattern of a non-negative float (order independent)
+__global__ void __launch_bounds__(256) absmax_flat_kernel(const float* __restrict__ a, int64_t n, unsigned* out_bits) {
+  float mx = 0.f;
+  const int64_t n4 = (reinterpret_cast<uintptr_t>(a) & 15) ? 0 : n >> 2;  // vector loads only when aligned
+  const float4* a4 = reinterpret_cast<const float4*>(a);
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n4; k += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(a4 + k);
+    const float m4 = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+    mx = (m4 == m4) ? fmaxf(mx, m4) : mx;
+  }
+  for (int64_t k = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+    const float v = fabsf(a[k]);
+    mx = (v == v) ? fmaxf(mx, v) : mx;
+  }
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0 && mx > 0.f) atomicMax(out_bits, __float_as_uint(mx));
+}
+
+__global__ void set_bits_kernel(unsigned* p, unsigned v) { *p = v; }
+
 static bool use_local_binning() {
   static const bool v = [] {
     const char* e = getenv("C2M_WARP_BWD_LISTS");  // tuning hook: 1 = global contributor lists also for channels-last
@@ -970,8 +1152,9 @@ int launch_bwd_gather(const BwdParams& pin, Layout lx, void* workspace, size_t w
   p.n0 = 0;
   p.nframes = d.N;
   p.key_mul = lx == LAYOUT_NHWC ? d.C / 4 : 1;  // channels-last lists address gout in 16-byte units
+  const bool det = (d.flags & C2M_FLAG_DETERMINISTIC) && p.gx;
   if (p.gx && local) {
-    const LocalWs w = carve_local(workspace, d.N, d.H, d.W, d.x_batch);
+    const LocalWs w = carve_local(workspace, d.N, d.H, d.W, d.x_batch, d.C, det);
     if (!workspace || workspace_bytes < w.bytes) {
       set_error("workspace too small: %zu < %zu", workspace_bytes, w.bytes);
       return C2M_ERR_WORKSPACE;
@@ -984,9 +1167,29 @@ int launch_bwd_gather(const BwdParams& pin, Layout lx, void* workspace, size_t w
     p.ovf_count = w.ovf_count;
     p.ovf_list = w.ovf_list;
     if (cudaMemsetAsync(w.tcnt, 0, w.clear_bytes, st) != cudaSuccess) return C2M_ERR_CUDA;
+    if (det) {
+      // fixed-point scale from max|gout| * max|mask| (a bound of every |term|), accumulator rows cleared
+      p.maxbits = w.maxbits;
+      p.touched = w.touched;
+      p.acc64 = w.acc64;
+      int cl = 2;  // 4 corners
+      const int64_t cnt = (int64_t)d.H * d.W * (d.N / d.x_batch);
+      while ((1ll << (cl - 2)) < cnt) ++cl;
+      p.count_log2 = cl;
+      if (cudaMemsetAsync(w.maxbits, 0, w.det_clear_bytes, st) != cudaSuccess) return C2M_ERR_CUDA;
+      const int64_t ng = (int64_t)d.N * d.C * d.H * d.W;
+      absmax_flat_kernel<<<sm_count() * 8, 256, 0, st>>>(p.gout, ng, w.maxbits);
+      if (p.mask) absmax_flat_kernel<<<sm_count() * 2, 256, 0, st>>>(p.mask, (int64_t)d.N * d.H * d.W, w.maxbits + 1);
+      else set_bits_kernel<<<1, 1, 0, st>>>(w.maxbits + 1, 0x3f800000u);
+      count_launch(2);
+    }
     const int64_t nseg = (int64_t)d.N * d.H * ((d.W + 31) / 32);
     segbin_kernel<<<(unsigned)((nseg + 7) / 8), 256, 0, st>>>(p);
     count_launch();
+    if (det) {  // incoherent segments / failed registrations first: the gather folds their rows in
+      overflow_kernel<true, true><<<sm_count() * 8, 256, 0, st>>>(p);
+      count_launch();
+    }
   } else if (p.gx) {
     const GatherWs w = carve(workspace, d.N, d.H, d.W, d.x_batch);
     if (!workspace || workspace_bytes < w.bytes) {
@@ -1006,7 +1209,14 @@ int launch_bwd_gather(const BwdParams& pin, Layout lx, void* workspace, size_t w
   if (lx == LAYOUT_NHWC) {
     BwdParams q = p;
     q.nframes = d.x_batch;  // a grad-input-only pass walks the images of x
-    if (local) {
+    if (local && det) {
+      if (fuse) {
+        launch_gather_nhwc_lp<true, true, true, true>(p, st);
+      } else {
+        launch_gather_nhwc_lp<true, false, true, true>(q, st);
+        if (need_gf) launch_gather_nhwc_lp<false, true, false>(p, st);
+      }
+    } else if (local) {
       if (fuse) {
         launch_gather_nhwc_lp<true, true, true>(p, st);
       } else {
@@ -1030,7 +1240,7 @@ int launch_bwd_gather(const BwdParams& pin, Layout lx, void* workspace, size_t w
     }
     if (need_gf) launch_gather_nchw<false, true, false>(p, st);
   }
-  if (p.gx) {
+  if (p.gx && !(local && det)) {
     const int grid = sm_count() * 8;
     if (lx == LAYOUT_NHWC)  // gather_supported() has checked C % 4 and the 16-byte alignment
       overflow_kernel<true><<<grid, 256, 0, st>>>(p);

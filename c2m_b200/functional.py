@@ -106,7 +106,7 @@ class WarpBlendFunction(torch.autograd.Function):
         gother = torch.empty_like(gout) if need_other else None
         if deterministic:
             flags |= _lib.FLAG_DETERMINISTIC
-        elif not nhwc and need_x and C % 4 == 0 and not (flags & _lib.FLAG_NO_STAGE):
+        if not nhwc and need_x and C % 4 == 0 and not (flags & _lib.FLAG_NO_STAGE):
             # NCHW tensors: the library stages them through channels-last copies in the workspace and runs
             # the channels-last kernels (about twice as fast as gathering 4-byte elements at NCHW strides)
             flags |= _lib.FLAG_STAGE_NHWC

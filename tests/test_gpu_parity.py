@@ -243,6 +243,22 @@ def test_deterministic_mode_is_bitwise_reproducible(dev, layout):
         for a, b in zip(runs[0][1], r[1]):
             assert torch.equal(a, b)
     check(runs[0], run_ref(x, flow, mask, gout))
+    # the generic fixed-point scatter (NCHW tensors kept on the NCHW kernels) is the other deterministic route
+    if layout == "nchw":
+        old = [run_ours(x, flow, mask, gout, deterministic=True, flags=_lib.FLAG_NO_STAGE) for _ in range(2)]
+        assert torch.equal(old[0][1][0], old[1][1][0])
+        check(old[0], run_ref(x, flow, mask, gout))
+    # a converging flow piles many contributions on few destinations: list overflow inside the gather
+    conv = flow.clone()
+    jj = torch.arange(conv.shape[3], device=dev, dtype=torch.float32).view(1, 1, -1)
+    ii = torch.arange(conv.shape[2], device=dev, dtype=torch.float32).view(1, -1, 1)
+    conv[:, 0] = (conv.shape[3] / 2 - jj) * 0.9 + torch.randn_like(conv[:, 0])
+    conv[:, 1] = (conv.shape[2] / 2 - ii) * 0.9 + torch.randn_like(conv[:, 1])
+    c1 = run_ours(x, conv, mask, gout, deterministic=True)
+    c2 = run_ours(x, conv, mask, gout, deterministic=True)
+    assert torch.equal(c1[1][0], c2[1][0])
+    check(c1, run_ref(x, conv, mask, gout))
+    check(run_ours(x, conv, mask, gout), run_ref(x, conv, mask, gout))
     # torch's global switch selects it too (the reference op raises under that switch)
     torch.use_deterministic_algorithms(True)
     try:
