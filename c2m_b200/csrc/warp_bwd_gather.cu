@@ -478,7 +478,7 @@ __device__ __forceinline__ void dot_finish(const DotRegs<NQ>& r, float& sa, floa
 //           atomics per contribution); otherwise they are read from the global lists bin_kernel wrote.
 //   DET     deterministic grad-input (local binning only): fixed-point integer accumulation
 template <int LP, int QI, bool DO_GX, bool DO_GF, bool HAS_MASK, bool USE_TMA, bool LOCAL, bool DET = false>
-__global__ void __launch_bounds__(256, 3) gather_nhwc_kernel(const __grid_constant__ BwdParams p,
+__global__ void __launch_bounds__(256, 4) gather_nhwc_kernel(const __grid_constant__ BwdParams p,
                                                              const __grid_constant__ CUtensorMap tm_flow,
                                                              const __grid_constant__ CUtensorMap tm_mask) {
   constexpr int TH = 8, TW = 32;
