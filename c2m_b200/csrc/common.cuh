@@ -68,7 +68,7 @@ struct BwdParams {
   int n0, nframes;          // the frames [n0, n0 + nframes) a launch covers
   // channels-last local binning (no global contributor lists): candidate row segments per destination tile
   int* tcnt;                // [x_batch * tiles] segments registered per destination tile
-  int* tlist;               // [x_batch * tiles][cand_cap] segment ids (n * H + i) * tiles_x + bx
+  int2* tlist;              // [x_batch * tiles][cand_cap] segments: (index of the first pixel, live pixels <= 32)
   int cand_cap;
   int4* pixrec;             // [N*H*W] per output pixel: (x0 | y0 << 16, ax, ay, mask) -- the sampling geometry,
                             // computed once by segbin_kernel and reused by every tile that bins the pixel

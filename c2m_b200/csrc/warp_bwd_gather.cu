@@ -115,12 +115,10 @@ __global__ void __launch_bounds__(256) segbin_kernel(const BwdParams p) {
   const int HW = d.H * d.W;
   const int tiles_x = (d.W + TW - 1) / TW, tiles_y = (d.H + TH - 1) / TH;
   const int lane = threadIdx.x & 31;
-  const int64_t nseg = (int64_t)d.N * d.H * tiles_x;
-  const int64_t seg = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (seg >= nseg) return;
-  const int bx = (int)(seg % tiles_x);
-  const int64_t r = seg / tiles_x;
-  const int i = (int)(r % d.H), n = (int)(r / d.H);
+  const int n = blockIdx.y;                                 // frame
+  const int rs = blockIdx.x * 8 + (threadIdx.x >> 5);       // segment within the frame
+  if (rs >= d.H * tiles_x) return;
+  const int i = rs / tiles_x, bx = rs - i * tiles_x;
   const int j = bx * TW + lane;
   const bool live = j < d.W;
   int xmin = INT_MAX, xmax = INT_MIN, ymin = INT_MAX, ymax = INT_MIN;
@@ -167,7 +165,8 @@ __global__ void __launch_bounds__(256) segbin_kernel(const BwdParams p) {
     if (lane < ncell) {
       const int dt = ((n % d.x_batch) * tiles_y + ty0 + lane / ncols) * tiles_x + tx0 + lane % ncols;
       const int slot = atomicAdd(p.tcnt + dt, 1);
-      if (slot < p.cand_cap) p.tlist[(int64_t)dt * p.cand_cap + slot] = (int)seg;
+      if (slot < p.cand_cap)
+        p.tlist[(int64_t)dt * p.cand_cap + slot] = make_int2(n * HW + i * d.W + bx * TW, min(TW, d.W - bx * TW));
       else ok = false;
     }
     fail = __ballot_sync(0xffffffffu, !ok);
@@ -549,24 +548,20 @@ __global__ void __launch_bounds__(256, 4) gather_nhwc_kernel(const __grid_consta
     __syncthreads();
     const int T = (n * tiles_y + by) * tiles_x + bx;  // destination tile (n: image of x)
     const int ncand = min(__ldg(p.tcnt + T), p.cand_cap);
-    const int* tl = p.tlist + (int64_t)T * p.cand_cap;
-    const int myid = (warp + 8 * lane < ncand) ? __ldg(tl + warp + 8 * lane) : 0;  // warp w takes c = w, w+8, ...
+    const int2* tl = p.tlist + (int64_t)T * p.cand_cap;
+    const int2 myid = (warp + 8 * lane < ncand) ? __ldg(tl + warp + 8 * lane) : make_int2(0, 0);  // warp w: c = w, w+8, ...
     const int nit = (ncand - warp + 7) >> 3;
     const float det_scale = DET ? fixed_scale_from(__uint_as_float(p.maxbits[0]) * __uint_as_float(p.maxbits[1]),
                                                    p.count_log2) : 1.f;
 #pragma unroll 2
     for (int it = 0; it < nit; ++it) {
-      const int seg = __shfl_sync(0xffffffffu, myid, it);
-      const int sbx = seg % tiles_x;
-      const int sr = seg / tiles_x;
-      const int si = sr % d.H, sn = sr / d.H;
-      const int sj = sbx * TW + lane;
+      const int seg0 = __shfl_sync(0xffffffffu, myid.x, it), nlive = __shfl_sync(0xffffffffu, myid.y, it);
       // deterministic mode: contributions that found their list full (bit k), kept for the warp-wide push below
       unsigned failbits = 0;
       int f_pos = 0, f_sidx = 0;
       float f_ax = 0.f, f_ay = 0.f, f_m = 0.f;
-      if (sj < d.W) {
-        const int sidx = (sn * d.H + si) * d.W + sj;
+      if (lane < nlive) {
+        const int sidx = seg0 + lane;
         const int4 rec = __ldg(p.pixrec + sidx);
         const int ux0 = (int)(short)(rec.x & 0xffff), uy0 = rec.x >> 16;
         // tile-local position of the nw corner; the four corners are (dy, dx), (dy, dx+1), (dy+1, dx), (dy+1, dx+1)
@@ -963,7 +958,7 @@ struct LocalWs {
   int* tcnt;
   int* ovf_count;
   unsigned char* ovf;
-  int* tlist;
+  int2* tlist;
   int* ovf_list;
   int4* pixrec;
   int cand_cap;
@@ -989,8 +984,8 @@ static LocalWs carve_local(void* base, int64_t N, int H, int W, int64_t x_batch,
   w.ovf = reinterpret_cast<unsigned char*>(b + o);
   o += up256(npix_o);
   w.clear_bytes = o;
-  w.tlist = reinterpret_cast<int*>(b + o);
-  o += up256(ntile * w.cand_cap * sizeof(int));
+  w.tlist = reinterpret_cast<int2*>(b + o);
+  o += up256(ntile * w.cand_cap * sizeof(int2));
   w.ovf_list = reinterpret_cast<int*>(b + o);
   o += up256(npix_o * sizeof(int));
   w.pixrec = reinterpret_cast<int4*>(b + o);
@@ -1038,6 +1033,7 @@ bool gather_supported(const BwdParams& p, Layout lx, Layout lg) {
       return false;
     if ((int64_t)d.H * d.W * d.C >= (1ll << 30)) return false;  // 32-bit byte offsets inside one image
     if (d.H >= 32768 || d.W >= 32768) return false;              // 16-bit corner coordinates in the pixel records
+    if (d.N > 65535) return false;                                // segbin_kernel puts the frame in gridDim.y
     if ((int64_t)d.N * d.H * d.W * (d.C / 4) >= (1ll << 32)) return false;  // 32-bit source keys (16-byte units)
   }
   return true;
@@ -1045,7 +1041,7 @@ bool gather_supported(const BwdParams& p, Layout lx, Layout lg) {
 
 template <int LP, int QI, bool DO_GX, bool DO_GF, bool LOCAL, bool DET>
 static void launch_gather_nhwc(BwdParams p, cudaStream_t st) {
-  p.pf_tiles = prefetch_tiles(0);  // measured: own tile, issued at CTA start, is the best distance
+  p.pf_tiles = prefetch_tiles(-1);  // measured: with four CTAs per SM resident the L2 prefetch gains nothing
   constexpr int TH = 8, TW = 32;
   const Dims& d = p.d;
   const int tiles = p.nframes * ((d.H + TH - 1) / TH) * ((d.W + TW - 1) / TW);
@@ -1183,8 +1179,8 @@ int launch_bwd_gather(const BwdParams& pin, Layout lx, void* workspace, size_t w
       else set_bits_kernel<<<1, 1, 0, st>>>(w.maxbits + 1, 0x3f800000u);
       count_launch(2);
     }
-    const int64_t nseg = (int64_t)d.N * d.H * ((d.W + 31) / 32);
-    segbin_kernel<<<(unsigned)((nseg + 7) / 8), 256, 0, st>>>(p);
+    const int segs = d.H * ((d.W + 31) / 32);  // per frame; grid.y = frames (N <= 65535 checked by gather_supported)
+    segbin_kernel<<<dim3((unsigned)((segs + 7) / 8), (unsigned)d.N), 256, 0, st>>>(p);
     count_launch();
     if (det) {  // incoherent segments / failed registrations first: the gather folds their rows in
       overflow_kernel<true, true><<<sm_count() * 8, 256, 0, st>>>(p);

@@ -91,12 +91,12 @@ def test_workspace_size_contract():
         256 + up(4 * (npix + 1 + 4)) + up(64 * npix) + up(npix) + up(4 * npix))
     assert _lib.bwd_workspace_bytes(4, 8, 16, 32, 4, True, _lib.FLAG_BWD_ATOMIC) == 256
     # deterministic: the larger of (a) one int64 per grad-input element (generic fixed-point scatter) and
-    # (b) the channels-last gather's bookkeeping (tile counters, overflow flags, candidate ids (96 per tile and
+    # (b) the channels-last gather's bookkeeping (tile counters, overflow flags, candidate segments (8 B each, 96 per tile and
     # source frame), overflow list, 16 B pixel records) + scale bits, touched flags and the int64 overflow rows
     def local_det(N, C, H, W, B):
         ntile, npo, npd = B * ((H + 7) // 8) * ((W + 31) // 32), N * H * W, B * H * W
         cap = min(256, 96 * (N // B))
-        return (up(4 * (ntile + 1)) + up(npo) + up(4 * ntile * cap) + up(4 * npo) + up(16 * npo)
+        return (up(4 * (ntile + 1)) + up(npo) + up(8 * ntile * cap) + up(4 * npo) + up(16 * npo)
                 + 256 + up(npd) + up(8 * npd * C))
     det = _lib.bwd_workspace_bytes(4, 8, 16, 32, 4, True, _lib.FLAG_DETERMINISTIC)
     assert det == 256 + max(4 * 8 * 16 * 32 * 8, local_det(4, 8, 16, 32, 4))
