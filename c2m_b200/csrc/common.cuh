@@ -92,32 +92,35 @@ __device__ __forceinline__ float base_coord(int k, int n, float step) {
   return (k < (n >> 1)) ? fmaf(step, (float)k, -1.f) : fmaf(-step, (float)(n - 1 - k), 1.f);
 }
 
+// PROBE keeps the run-time switches of tools/probe.py (true division / unfused multiply-add); the layout-
+// specialised kernels compile them out (launchers send such calls to the generic kernels).
+template <bool PROBE>
 __device__ __forceinline__ float unnormalized(float f, int k, int n, float step, float inv_b, float b,
                                               int flags) {
   const float g = base_coord(k, n, step);
   // intrinsics keep nvcc from contracting across the reference's materialised temporaries
-  const float nf = (flags & C2M_FLAG_TRUE_DIV) ? __fdiv_rn(f, b) : __fmul_rn(f, inv_b);
+  const float nf = (PROBE && (flags & C2M_FLAG_TRUE_DIV)) ? __fdiv_rn(f, b) : __fmul_rn(f, inv_b);
   const float c1 = __fadd_rn(__fadd_rn(g, nf), 1.f);
-  const float u = (flags & C2M_FLAG_NO_FMA) ? __fadd_rn(__fmul_rn(c1, (float)n), -1.f)
-                                            : fmaf(c1, (float)n, -1.f);
+  const float u = (PROBE && (flags & C2M_FLAG_NO_FMA)) ? __fadd_rn(__fmul_rn(c1, (float)n), -1.f)
+                                                       : fmaf(c1, (float)n, -1.f);
   return u * 0.5f;
 }
 
 // BWD selects ATen's clip_coordinates_set_grad behaviour (NaN is not clipped there and ends up at
 // -100 through safe_downgrade_to_int_range, GridSampler.cuh:64-82,141-148).
-template <bool BWD>
+template <bool BWD, bool PROBE = false>
 __device__ __forceinline__ void make_geo(const Dims& d, float fx, float fy, int i, int j, Geo& g) {
   float ix, iy;
   float sx = d.inv_bw, sy = d.inv_bh;
-  if (d.flags & C2M_FLAG_COORD_GRID) {
+  if (PROBE && (d.flags & C2M_FLAG_COORD_GRID)) {
     // (fx, fy) is a normalised sampling location (reference utils.grid_sample, ops.py:183-184)
     ix = fmaf(__fadd_rn(fx, 1.f), (float)d.W, -1.f) * 0.5f;
     iy = fmaf(__fadd_rn(fy, 1.f), (float)d.H, -1.f) * 0.5f;
     sx = 1.f;
     sy = 1.f;
   } else {
-    ix = unnormalized(fx, j, d.W, d.stepx, d.inv_bw, d.bw, d.flags);
-    iy = unnormalized(fy, i, d.H, d.stepy, d.inv_bh, d.bh, d.flags);
+    ix = unnormalized<PROBE>(fx, j, d.W, d.stepx, d.inv_bw, d.bw, d.flags);
+    iy = unnormalized<PROBE>(fy, i, d.H, d.stepy, d.inv_bh, d.bh, d.flags);
   }
   float cgx = 1.f, cgy = 1.f;
   if (d.padding == C2M_PAD_BORDER) {

@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(256) bwd_scatter_kernel(const BwdParams p) {
     const float fx = fl[0], fy = fl[gridmode ? 1 : HW];
     const float m = p.mask ? p.mask[(int64_t)n * HW + r] : 1.f;
     Geo g;
-    make_geo<true>(d, fx, fy, i, j, g);
+    make_geo<true, true>(d, fx, fy, i, j, g);
     const int64_t xbase = (int64_t)(n % d.x_batch) * p.xs[0];
     const int64_t onw = g.y0 * p.xs[2] + g.x0 * p.xs[3], one = g.y0 * p.xs[2] + g.x1 * p.xs[3];
     const int64_t osw = g.y1 * p.xs[2] + g.x0 * p.xs[3], ose = g.y1 * p.xs[2] + g.x1 * p.xs[3];

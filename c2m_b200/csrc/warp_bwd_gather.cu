@@ -1022,7 +1022,8 @@ static bool use_local_binning();
 
 bool gather_supported(const BwdParams& p, Layout lx, Layout lg) {
   const Dims& d = p.d;
-  if (d.flags & (C2M_FLAG_BWD_ATOMIC | C2M_FLAG_FORCE_GENERIC | C2M_FLAG_COORD_GRID)) return false;
+  if (d.flags & (C2M_FLAG_BWD_ATOMIC | C2M_FLAG_FORCE_GENERIC | C2M_FLAG_COORD_GRID | C2M_FLAG_TRUE_DIV | C2M_FLAG_NO_FMA))
+    return false;
   // deterministic grad-input: only the channels-last local-binning gather has an order-independent form
   if ((d.flags & C2M_FLAG_DETERMINISTIC) && p.gx && !(lx == LAYOUT_NHWC && use_local_binning())) return false;
   if (p.other || p.gother) return false;

@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(256) fwd_generic_kernel(const FwdParams p) {
     const float fx = fl[0], fy = fl[gridmode ? 1 : HW];
     const float m = p.mask ? p.mask[(int64_t)n * HW + r] : 1.f;
     Geo g;
-    make_geo<false>(d, fx, fy, i, j, g);
+    make_geo<false, true>(d, fx, fy, i, j, g);
     const float* xb = p.x + (int64_t)(n % d.x_batch) * p.xs[0];
     const int64_t onw = g.y0 * p.xs[2] + g.x0 * p.xs[3], one = g.y0 * p.xs[2] + g.x1 * p.xs[3];
     const int64_t osw = g.y1 * p.xs[2] + g.x0 * p.xs[3], ose = g.y1 * p.xs[2] + g.x1 * p.xs[3];
@@ -337,7 +337,8 @@ static int launch_nhwc(const FwdParams& p, cudaStream_t st) {
 
 int launch_fwd(const FwdParams& p, Layout lx, Layout lo, cudaStream_t st) {
   const Dims& d = p.d;
-  const bool generic = (d.flags & (C2M_FLAG_FORCE_GENERIC | C2M_FLAG_COORD_GRID)) || p.other != nullptr || lx != lo ||
+  const bool generic = (d.flags & (C2M_FLAG_FORCE_GENERIC | C2M_FLAG_COORD_GRID | C2M_FLAG_TRUE_DIV | C2M_FLAG_NO_FMA)) ||
+                       p.other != nullptr || lx != lo ||
                        lx == LAYOUT_OTHER || (int64_t)d.H * d.W >= (1ll << 30);
   if (!generic && lx == LAYOUT_NCHW) {
     const int variant = (d.flags >> 16) & 0xf;  // tuning hook (bench sweeps); 0 = default
