@@ -152,8 +152,55 @@ size_t bwd_workspace_bytes(int64_t N, int C, int H, int W, int64_t x_batch, int 
 }
 
 // ---------------------------------------------------------------------------------------------
-// NCHW <-> channels-last staging copies ([n][c][hw] <-> [n][hw][c]) through a 32 x 33 shared-memory tile:
-// both sides move 128-byte rows.
+// NCHW <-> channels-last staging copies ([n][c][hw] <-> [n][hw][c]) through a 64 x 65 shared-memory tile,
+// 128-bit global accesses on both sides (C % 4 == 0, HW % 4 == 0 and 16-byte aligned tensors; transpose_kernel
+// below is the scalar fallback).
+template <bool TO_NHWC>
+__global__ void __launch_bounds__(256) transpose64_kernel(const float* __restrict__ in, float* __restrict__ out, int C,
+                                                          int HW) {
+  __shared__ float tile[64][65];  // [channel][pixel]
+  const int t = threadIdx.x;
+  const int64_t img = (int64_t)blockIdx.z * C * HW;
+  const int c0 = blockIdx.y * 64, p0 = blockIdx.x * 64;
+  const int a = t >> 4, b4 = (t & 15) * 4;  // 16 rows per pass, one float4 column group per thread
+  if (TO_NHWC) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {  // rows = channels, columns = pixels
+      const int c = c0 + a + 16 * k, px = p0 + b4;
+      if (c < C && px < HW) {
+        const float4 v = __ldcs(reinterpret_cast<const float4*>(in + img + (int64_t)c * HW + px));
+        tile[a + 16 * k][b4] = v.x; tile[a + 16 * k][b4 + 1] = v.y; tile[a + 16 * k][b4 + 2] = v.z; tile[a + 16 * k][b4 + 3] = v.w;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {  // rows = pixels, columns = channels
+      const int px = p0 + a + 16 * k, c = c0 + b4;
+      if (c < C && px < HW)
+        *reinterpret_cast<float4*>(out + img + (int64_t)px * C + c) =
+            make_float4(tile[b4][a + 16 * k], tile[b4 + 1][a + 16 * k], tile[b4 + 2][a + 16 * k], tile[b4 + 3][a + 16 * k]);
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int px = p0 + a + 16 * k, c = c0 + b4;
+      if (c < C && px < HW) {
+        const float4 v = __ldcs(reinterpret_cast<const float4*>(in + img + (int64_t)px * C + c));
+        tile[b4][a + 16 * k] = v.x; tile[b4 + 1][a + 16 * k] = v.y; tile[b4 + 2][a + 16 * k] = v.z; tile[b4 + 3][a + 16 * k] = v.w;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = c0 + a + 16 * k, px = p0 + b4;
+      if (c < C && px < HW)
+        __stcs(reinterpret_cast<float4*>(out + img + (int64_t)c * HW + px),
+               make_float4(tile[a + 16 * k][b4], tile[a + 16 * k][b4 + 1], tile[a + 16 * k][b4 + 2], tile[a + 16 * k][b4 + 3]));
+    }
+  }
+}
+
+// scalar fallback: 32 x 33 tile, 128-byte rows both ways
 template <bool TO_NHWC>
 __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int C,
                                                         int HW) {
@@ -190,8 +237,14 @@ __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict_
 
 template <bool TO_NHWC>
 static void launch_transpose(const float* in, float* out, int64_t n, int C, int HW, cudaStream_t st) {
-  const dim3 grid((HW + 31) / 32, (C + 31) / 32, (unsigned)n);
-  transpose_kernel<TO_NHWC><<<grid, 256, 0, st>>>(in, out, C, HW);
+  const bool vec = (C % 4) == 0 && (HW % 4) == 0 && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  if (vec) {
+    const dim3 grid((HW + 63) / 64, (C + 63) / 64, (unsigned)n);
+    transpose64_kernel<TO_NHWC><<<grid, 256, 0, st>>>(in, out, C, HW);
+  } else {
+    const dim3 grid((HW + 31) / 32, (C + 31) / 32, (unsigned)n);
+    transpose_kernel<TO_NHWC><<<grid, 256, 0, st>>>(in, out, C, HW);
+  }
   count_launch();
 }
 
