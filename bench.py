@@ -176,9 +176,8 @@ def run_reference(args):
 
 
 def run_ours(args):
-    # rank 0 prints exactly one line on stdout: keep NCCL's version banner off it
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # rank 0 prints exactly one line on stdout: NCCL's own messages (version banner) go to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import c2m_b200
     from c2m_b200 import _lib
     from c2m_b200 import dist as cdist

@@ -105,3 +105,107 @@ def patch_reference(verbose: bool = False):
         for d in done:
             print("c2m_b200: patched %s.%s" % d)
     return done
+
+
+# ------------------------------------------------------------------------------------------------
+# Host module: the reference's occlusion-aware generator with the fused warp swapped in.
+#
+# Same constructor, same forward signature and -- attribute for attribute -- the same state-dict keys as
+# /root/reference/src/modules/generator/generator.py:11-158 (blocks: src/modules/layers/same_block.py:5-23,
+# down_block.py:5-24, up_block.py:5-27, residual_block.py:6-31), so reference checkpoints load unchanged
+# (SURVEY.md appendix B).  The convolutions / norms stay ordinary PyTorch (cuDNN); only the two warp call
+# sites (generator.py:135-137 and :140-145) run the sm_100a kernels.  The SPADE variant (use_spade=True:
+# FlowEmbedder + spatially adaptive norms) is not rebuilt here; patch the reference class instead
+# (patch_reference) when that variant is needed.
+from torch import nn  # noqa: E402
+
+
+class _ConvNormLeaky(nn.Module):
+    """conv -> norm -> LeakyReLU(0.2); `norm` is 'instance' (affine) or 'batch'."""
+
+    def __init__(self, cin, cout, kernel_size, stride, padding, padding_mode, norm):
+        super().__init__()
+        self.conv = nn.Conv2d(cin, cout, kernel_size, stride, padding, padding_mode=padding_mode)
+        self.norm = nn.InstanceNorm2d(cout, affine=True) if norm == "instance" else nn.BatchNorm2d(cout)
+
+    def forward(self, x):
+        return F.leaky_relu(self.norm(self.conv(x)), 0.2)
+
+
+class _PreActResidual(nn.Module):
+    """BN -> ReLU -> reflect-pad conv, twice, plus the input."""
+
+    def __init__(self, planes, kernel_size, padding):
+        super().__init__()
+        self.padding = nn.ReflectionPad2d(padding)
+        self.conv1 = nn.Conv2d(planes, planes, kernel_size)
+        self.conv2 = nn.Conv2d(planes, planes, kernel_size)
+        self.norm1 = nn.BatchNorm2d(planes)
+        self.norm2 = nn.BatchNorm2d(planes)
+
+    def forward(self, x):
+        y = self.conv1(self.padding(F.relu(self.norm1(x))))
+        y = self.conv2(self.padding(F.relu(self.norm2(y))))
+        return y + x
+
+
+class _UpsampleConv(nn.Module):
+    """x2 bilinear upsample -> conv -> BN -> LeakyReLU(0.2) (parameters live under `main.1` / `main.2`)."""
+
+    def __init__(self, cin, cout, kernel_size, padding, padding_mode):
+        super().__init__()
+        self.main = nn.Sequential(nn.Upsample(scale_factor=2, mode="bilinear"),
+                                  nn.Conv2d(cin, cout, kernel_size, 1, padding, padding_mode=padding_mode),
+                                  nn.BatchNorm2d(cout), nn.LeakyReLU(0.2, inplace=True))
+
+    def forward(self, x):
+        return self.main(x)
+
+
+class OcclusionAwareGenerator(nn.Module):
+    """Drop-in for the reference generator (non-SPADE variants, `dataset` 'cityscapes' or '...kitti...')."""
+
+    def __init__(self, model_params, flow_params, input_channel, dataset):
+        super().__init__()
+        if model_params.get("use_spade", False):
+            raise NotImplementedError("use_spade=True is not rebuilt in c2m_b200; use patch_reference() on the reference class")
+        be, nd = model_params["block_expansion"], model_params["num_down_blocks"]
+        cap, pm = model_params["max_expansion"], model_params["padding_mode"]
+        self.num_down_blocks, self.dataset, self.flow_params = nd, dataset, flow_params
+        width = lambda k: min(cap, be * (2 ** k))  # noqa: E731
+
+        def encoder():
+            first = _ConvNormLeaky(input_channel, be, 7, 1, 3, pm, "instance")
+            downs = [_ConvNormLeaky(width(k), width(k + 1), 4, 2, 1, pm, "batch") for k in range(nd)]
+            return first, downs
+
+        self.first, downs = encoder()
+        self.down_blocks = nn.ModuleList(downs)
+        if "kitti" in dataset:  # second encoder on the warped frame, merged before decoding
+            self.first_warped, downs_w = encoder()
+            self.down_blocks_warped = nn.Sequential(*downs_w)
+            self.pre_decode = nn.Sequential(_ConvNormLeaky(2 * width(nd), width(nd), 3, 1, 1, pm, "instance"))
+        self.up_blocks = nn.ModuleList([_UpsampleConv(width(nd - k), width(nd - k - 1), 3, 1, pm) for k in range(nd)])
+        self.middle = nn.Sequential(*[_PreActResidual(width(nd), 3, 1) for _ in range(model_params["num_bottleneck_blocks"])])
+        self.final = nn.Sequential(nn.Conv2d(be, 3, kernel_size=7, padding=3), nn.Sigmoid())
+
+    deform_input = staticmethod(deform_input)
+    apply_optical = apply_optical
+
+    def forward(self, first_frame, flow, occlusion_map):
+        out = self.first(first_frame)
+        for blk in self.down_blocks:
+            out = blk(out)
+        out = self.apply_optical(input_ref=out, optical_flow=flow, occlusion_map=occlusion_map)  # fused warp * mask
+        out = self.middle(out)
+        if "kitti" in self.dataset:
+            warped = self.apply_optical(input_ref=first_frame, optical_flow=flow, occlusion_map=None)
+            warped = self.down_blocks_warped(self.first_warped(warped))
+            if warped.shape[2:] != occlusion_map.shape[2:]:
+                occlusion_map = F.interpolate(occlusion_map, size=warped.shape[2:], mode="bilinear")
+            out = self.pre_decode(torch.cat([out, warped * occlusion_map], dim=1))
+        for blk in self.up_blocks:
+            out = blk(out)
+        if out.shape[-2:] != first_frame.shape[-2:]:
+            out = F.interpolate(out, list(first_frame.shape[-2:]), mode="bilinear")
+        return self.final(out)

@@ -1,2 +1,2 @@
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -8 > gpurun_out/r2l_pytest.log
-timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --e2e-steps 0 --layout nchw --no-other-layout > gpurun_out/r2l_bench_nchw.json 2> gpurun_out/r2l_bench_nchw.err
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29521 tools/bench_generator.py > gpurun_out/r2n_gen_g2.json 2> gpurun_out/r2n_gen_g2.err
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29522 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r2n_bench_g2.json 2> gpurun_out/r2n_bench_g2.err
