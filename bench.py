@@ -267,6 +267,71 @@ def run_ours(args):
                  "achieved": oach}
         del x2, g2
 
+    # ---- secondary figures: the multi-scale sites of the reference, N frames each, all levels of
+    # a pyramid run back to back (small levels are launch-bound: reported as they are, not as roofline evidence)
+    pyramids = None
+    if args.pyramids:
+        sets = {
+            "generator_encoder": [(32, 256, 512), (64, 128, 256), (128, 64, 128), (256, 32, 64)],
+            "motion_decoder": [(64, 64, 128), (128, 32, 64), (256, 16, 32), (512, 8, 16)],
+            "image": [(3, 256, 512)],
+        }
+        pyramids = {}
+        for name, levels in sets.items():
+            ts = []
+            for (c, h, w) in levels:
+                px, pf, pm, pg = synth(N, c, h, w, False, 77 + rank, dev)
+                if nhwc and c % 4 == 0:
+                    px, pg = px.contiguous(memory_format=torch.channels_last), pg.contiguous(memory_format=torch.channels_last)
+                ts.append((px.requires_grad_(True), pf.requires_grad_(True), pm.requires_grad_(True), pg))
+
+            def pstep():
+                for (px, pf, pm, pg) in ts:
+                    o = c2m_b200.warp_blend(px, pf, pm)
+                    torch.autograd.grad(o, [px, pf, pm], pg)
+
+            for _ in range(2):
+                pstep()
+            barrier()
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            p0.record()
+            for _ in range(5):
+                pstep()
+            p1.record()
+            barrier()
+            pms = p0.elapsed_time(p1) / 5
+            pbytes = sum(fwd_bytes(N, c, h, w) + bwd_bytes(N, c, h, w) for (c, h, w) in levels)
+            pyramids[name] = {"levels": [list(l) for l in levels], "ms": pms, "achieved": pbytes / (pms * 1e-3) / 1e9}
+            del ts
+
+    # ---- comparative figure: the reference's own GPU path (ops.py:187-202 + generator.py:93 as the unpatched
+    # trainer runs it: CPU-built grid copied to the device every call, div / cat / add, grid_sample, multiply)
+    torch_cuda = None
+    if args.torch_cuda_steps > 0:
+        import torch.nn.functional as F
+
+        def ref_step():
+            g0 = torch.zeros([N, 2, H, W])
+            g0[:, 0] = torch.linspace(-1, 1, W).view(1, 1, W).expand(N, H, W)
+            g0[:, 1] = torch.linspace(-1, 1, H).view(1, H, 1).expand(N, H, W)
+            g0 = g0.to(dev)
+            nf = torch.cat([flow[:, 0:1] / ((W - 1.0) / 2.0), flow[:, 1:2] / ((H - 1.0) / 2.0)], dim=1)
+            o = F.grid_sample(x, (g0 + nf).permute(0, 2, 3, 1), mode="bilinear", padding_mode="border",
+                              align_corners=False) * mask
+            torch.autograd.grad(o, [x, flow, mask], gout)
+
+        ref_step()
+        barrier()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        for _ in range(args.torch_cuda_steps):
+            ref_step()
+        r1.record()
+        barrier()
+        rms = r0.elapsed_time(r1) / args.torch_cuda_steps
+        torch_cuda = {"ms_per_step": rms, "frames_per_s_per_gpu": N / (rms * 1e-3),
+                      "what": "torch %s CUDA composition of the reference path on the same tensors (comparison only)" % torch.__version__}
+
     e2e = None
     if args.e2e_steps > 0:
         hx, hflow, hmask, hgout = synth(N, C, H, W, oob, 1234 + rank, dev, pin=True)
@@ -307,6 +372,10 @@ def run_ours(args):
     if other is not None:
         other["frac"] = other["achieved"] / peak
         roof["other_layout"] = other
+    if pyramids is not None:
+        for v in pyramids.values():
+            v["frac"] = v["achieved"] / peak
+        roof["pyramids"] = pyramids
     tr = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tr):
         try:
@@ -331,7 +400,7 @@ def run_ours(args):
                        "grads": "input+flow+mask", "deterministic": det,
                        "l2": "inputs (%.0f MB per tensor) larger than L2, no flush needed" % (4e-6 * N * C * H * W),
                        "partition": "batch x frame, %d frames per rank, no collective" % N},
-            "roofline": roof, "cpu_baseline": cpu,
+            "roofline": roof, "cpu_baseline": cpu, "torch_cuda_reference": torch_cuda,
             "e2e": e2e,
             "gpu_launches": launches, "clocks": clk.summary(),
         }
@@ -357,6 +426,8 @@ def main():
     ap.add_argument("--flags", default="0")
     ap.add_argument("--cpu-frames", type=int, default=8, help="frames in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pyramids", dest="pyramids", action="store_false", help="skip the multi-scale secondary figures")
+    ap.add_argument("--torch-cuda-steps", type=int, default=3, help="steps of the torch CUDA composition (0: skip)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--e2e-chunks", type=int, default=8)
     args = ap.parse_args()

@@ -6,7 +6,7 @@ python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${T}_smoke.log 2
 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 > gpurun_out/${T}_pytest.log
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${T}_bench_ref.json 2> gpurun_out/${T}_bench_ref.err
 python bench.py > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err
-BENCH="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 0 --no-other-layout"
+BENCH="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 0 --no-other-layout --no-pyramids --torch-cuda-steps 0"
 $BENCH > gpurun_out/${T}_plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 400 --csv \
     --log-file gpurun_out/${T}_launches.csv $BENCH > gpurun_out/${T}_ncu_launches.log 2>&1

@@ -2,7 +2,7 @@
 VAR=$1; shift
 for v in "$@"; do
   echo "== $VAR=$v"
-  env $VAR=$v python bench.py --steps 10 --warmup 3 --layout nhwc --no-cpu-baseline --e2e-steps 0 2>&1 | python -c "
+  env $VAR=$v python bench.py --steps 10 --warmup 3 --layout nhwc --no-cpu-baseline --e2e-steps 0 --no-other-layout --no-pyramids --torch-cuda-steps 0 2>&1 | python -c "
 import json,sys
 for l in sys.stdin:
     if l.startswith('{'):
