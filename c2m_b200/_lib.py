@@ -34,6 +34,8 @@ SYMBOLS = (
     "c2m_warp_bwd_workspace_bytes",
     "c2m_base_grid",
     "c2m_warp_launch_count",
+    "c2m_occlusion_map",
+    "c2m_occlusion_map_workspace_bytes",
 )
 
 _lock = threading.Lock()
@@ -84,6 +86,10 @@ def load(build_if_missing: bool = False) -> ctypes.CDLL:
         lib.c2m_warp_bwd_workspace_bytes.argtypes = [_i64, _int, _int, _int, _i64, _int, _int]
         lib.c2m_base_grid.restype = _int
         lib.c2m_base_grid.argtypes = [_ptr, _i64, _int, _int, _ptr]
+        lib.c2m_occlusion_map_workspace_bytes.restype = ctypes.c_size_t
+        lib.c2m_occlusion_map_workspace_bytes.argtypes = [_i64, _int, _int]
+        lib.c2m_occlusion_map.restype = _int
+        lib.c2m_occlusion_map.argtypes = [_ptr, _ptr, _i64, _int, _int, _int, _ptr, ctypes.c_size_t, _ptr]
         _lib = lib
     return _lib
 
@@ -119,6 +125,18 @@ def bwd_workspace_bytes(N, C, H, W, x_batch, want_gx, flags) -> int:
 
 def base_grid(grid_ptr, N, H, W, stream) -> None:
     _check(load().c2m_base_grid(grid_ptr, N, H, W, stream), "c2m_base_grid")
+
+
+OCC_COORDS = 0x1
+OCC_NO_CLAMP = 0x2
+
+
+def occlusion_map(in_ptr, out_ptr, N, H, W, flags, ws_ptr, ws_bytes, stream) -> None:
+    _check(load().c2m_occlusion_map(in_ptr, out_ptr, N, H, W, flags, ws_ptr, ws_bytes, stream), "c2m_occlusion_map")
+
+
+def occlusion_map_workspace_bytes(N, H, W) -> int:
+    return int(load().c2m_occlusion_map_workspace_bytes(N, H, W))
 
 
 def launch_count() -> int:

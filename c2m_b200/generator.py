@@ -17,7 +17,7 @@ import torch
 import torch.nn.functional as F
 
 from .functional import warp_blend
-from .ops import get_grid, grid_sample, resample
+from .ops import get_corresponding_map, get_grid, get_occlusion_map, grid_sample, resample
 
 
 def _flow_for(inp: torch.Tensor, optical_flow: torch.Tensor) -> torch.Tensor:
@@ -78,6 +78,11 @@ _PATCH_TARGETS = (
     ("utils", "resample"),
     ("utils", "grid_sample"),
     ("utils", "get_grid"),
+    ("utils.ops", "get_occlusion_map"),
+    ("utils.ops", "get_corresponding_map"),
+    ("utils", "get_occlusion_map"),
+    ("utils", "get_corresponding_map"),
+    ("modules.third_party.flow_net.flow_net", "get_occlusion_map"),
     ("modules.generator.generator", "resample"),
     ("modules.motion_estimator.motion_autoencoder", "resample"),
     ("losses.losses", "resample"),
@@ -88,7 +93,8 @@ def patch_reference(verbose: bool = False):
     """Swap the fused kernels into an already-imported, unmodified C2M source tree.  Returns the
     list of (module, attribute) pairs that were replaced.  The trainer / test.py then run
     unchanged (INTEGRATION.md)."""
-    repl = {"resample": resample, "grid_sample": grid_sample, "get_grid": get_grid}
+    repl = {"resample": resample, "grid_sample": grid_sample, "get_grid": get_grid,
+            "get_occlusion_map": get_occlusion_map, "get_corresponding_map": get_corresponding_map}
     done = []
     for mod_name, attr in _PATCH_TARGETS:
         mod = sys.modules.get(mod_name)

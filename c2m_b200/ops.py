@@ -15,7 +15,7 @@ import torch
 from . import _lib
 from .functional import WarpBlendFunction, deterministic_default, warp_blend
 
-__all__ = ["resample", "grid_sample", "get_grid", "warp_blend"]
+__all__ = ["resample", "grid_sample", "get_grid", "warp_blend", "get_occlusion_map", "get_corresponding_map"]
 
 
 def _check_mode(mode: str) -> None:
@@ -91,6 +91,35 @@ def get_grid(batchsize: int, rows: int, cols: int, gpu_id=0) -> torch.Tensor:
     with torch.cuda.device(device):
         _lib.base_grid(grid.data_ptr(), batchsize, rows, cols, torch.cuda.current_stream().cuda_stream)
     return grid
+
+
+def _splat(data: torch.Tensor, flags: int) -> torch.Tensor:
+    if data.dim() != 4 or data.shape[1] != 2:
+        raise ValueError(f"expected [B,2,H,W], got {tuple(data.shape)}")
+    if not data.is_cuda or data.dtype != torch.float32:
+        raise RuntimeError("c2m_b200: float32 CUDA tensors required (no CPU fallback)")
+    d = data.detach().contiguous()
+    B, _, H, W = d.shape
+    out = torch.empty((B, 1, H, W), dtype=torch.float32, device=d.device)
+    with torch.cuda.device(d.device):
+        nbytes = _lib.occlusion_map_workspace_bytes(B, H, W)
+        ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=d.device)
+        _lib.occlusion_map(d.data_ptr(), out.data_ptr(), B, H, W, flags, ws.data_ptr(), nbytes,
+                           torch.cuda.current_stream().cuda_stream)
+    return out
+
+
+def get_corresponding_map(data: torch.Tensor) -> torch.Tensor:
+    """ops.py:205-251: `data` [B,2,H,W] absolute pixel coordinates -> [B,1,H,W] sum of the bilinear splat weights
+    that land on each pixel (corners outside the image dropped).  One scatter kernel with order-independent
+    fixed-point accumulation instead of eight temporaries + scatter_add_."""
+    return _splat(data, _lib.OCC_COORDS | _lib.OCC_NO_CLAMP)
+
+
+def get_occlusion_map(flow: torch.Tensor) -> torch.Tensor:
+    """ops.py:263-275: forward-splat the pixel `flow` [B,2,H,W] and clamp to [0, 1] (0 = occluded / nothing lands
+    there).  Like the reference it carries no gradient (ops.py:271 runs under no_grad)."""
+    return _splat(flow, 0)
 
 
 # re-exported so `from c2m_b200.ops import *` mirrors `from utils.ops import *`

@@ -12,6 +12,8 @@
  *                        backward, div/cat/add backward) -- the reference has no source for it.
  *   c2m_base_grid        src/utils/ops.py:196-202 `get_grid` (device-side, bit-identical to the
  *                        CPU-built float32 linspace grid).
+ *   c2m_occlusion_map    src/utils/ops.py:205-275 `get_corresponding_map` / `get_occlusion_map` (the forward
+ *                        splat that produces the warp's mask, dense_motion.py:148,151).
  *
  * The reference's own native-operator convention (its only hand-written warp,
  * src/modules/third_party/resample2d/src/resample2d_cuda.cc:6-33) is followed where it makes
@@ -99,6 +101,17 @@ C2M_API size_t c2m_warp_bwd_workspace_bytes(int64_t N, int C, int H, int W, int6
 
 /* [N,2,H,W] base grid, bit-identical to the reference's CPU float32 construction. */
 C2M_API int c2m_base_grid(float* grid, int64_t N, int H, int W, void* cuda_stream);
+
+/* Forward-splat occlusion map, the producer of the warp's mask (reference src/utils/ops.py:263-275
+ * `get_occlusion_map`; with C2M_OCC_COORDS | C2M_OCC_NO_CLAMP: ops.py:205-251 `get_corresponding_map`).
+ * in [N,2,H,W] contiguous (flow in pixels, or absolute coordinates), out [N,1,H,W].  The sum is accumulated in
+ * 64-bit fixed point: bitwise reproducible, unlike the reference's scatter_add_.  workspace:
+ * c2m_occlusion_map_workspace_bytes() bytes. */
+#define C2M_OCC_COORDS 0x1   /* `in` holds absolute pixel coordinates instead of a flow */
+#define C2M_OCC_NO_CLAMP 0x2 /* do not clamp the sum to [0, 1] */
+C2M_API size_t c2m_occlusion_map_workspace_bytes(int64_t N, int H, int W);
+C2M_API int c2m_occlusion_map(const float* in, float* out, int64_t N, int H, int W, int flags, void* workspace,
+                              size_t workspace_bytes, void* cuda_stream);
 
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
 C2M_API uint64_t c2m_warp_launch_count(void);

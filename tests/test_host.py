@@ -61,6 +61,7 @@ def test_patch_reference_rebinds_every_bound_name(monkeypatch):
     sentinel = object()
     for m in ("utils", "utils.ops"):
         fake[m].resample = fake[m].grid_sample = fake[m].get_grid = sentinel
+        fake[m].get_occlusion_map = fake[m].get_corresponding_map = sentinel
     for m in ("modules.generator.generator", "modules.motion_estimator.motion_autoencoder", "losses.losses"):
         fake[m].resample = sentinel
 
@@ -74,7 +75,8 @@ def test_patch_reference_rebinds_every_bound_name(monkeypatch):
 
     fake["modules.generator.generator"].OcclusionAwareGenerator = OcclusionAwareGenerator
     done = c2m_b200.patch_reference()
-    assert len(done) == 10
+    assert len(done) == 14
+    assert fake["utils"].get_occlusion_map is c2m_b200.get_occlusion_map
     assert fake["utils.ops"].resample is c2m_b200.resample
     assert fake["utils"].get_grid is c2m_b200.get_grid
     assert fake["losses.losses"].resample is c2m_b200.resample
