@@ -10,6 +10,8 @@
 //                         red.add (fp32) or, in deterministic mode, by order-independent 64-bit
 //                         fixed-point atomics into a workspace that fix2float_kernel converts.
 //   absmax_kernel         max |gout * mask| (sets the fixed-point scale; order independent).
+//   transpose*_kernel     NCHW <-> channels-last staging copies (C2M_FLAG_STAGE_NHWC).
+// launch_bwd() routes a call: channels-last / staged NCHW -> warp_bwd_gather.cu; everything else here.
 #include "common.cuh"
 
 namespace c2m {

@@ -9,10 +9,11 @@
 //                       (cp.async.bulk.tensor.3d, double buffered, mbarrier-signalled) one tile
 //                       ahead; one thread per pixel, channel loop unrolled for memory-level
 //                       parallelism; stores are 128-byte coalesced along W.
-//   fwd_nhwc_kernel     channels-last; same tile walk and TMA staging; a thread-per-pixel pass
-//                       writes the tile's geometry to shared memory, then LP lanes per pixel move
-//                       float4 channel groups: four 128-bit corner loads + one 128-bit store, every
-//                       access a full 16-byte-per-lane coalesced segment whatever the flow does.
+//   fwd_nhwc_kernel     channels-last; one CTA per 8 x 32 tile (non-persistent), flow/mask tile by TMA;
+//                       warp w owns tile row w: lane t writes the geometry of pixel t to the warp's
+//                       shared-memory slice, then LP lanes per pixel move float4 channel groups: four
+//                       128-bit corner loads + one 128-bit store, every access a full 16-byte-per-lane
+//                       coalesced segment whatever the flow does.
 #include "common.cuh"
 
 namespace c2m {

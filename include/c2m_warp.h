@@ -87,8 +87,9 @@ C2M_API int c2m_warp_blend_fwd(const float* x, const float* flow, const float* m
 
 /* Any of gx / gflow / gmask / gother may be NULL (<=> ctx.needs_input_grad false).  gx is fully
  * written by the call (zero-filled first when the scatter uses atomics); it has x's strides.
- * gout and gother have g_strides.  workspace: c2m_warp_bwd_workspace_bytes() bytes, 256-byte
- * aligned, contents undefined on entry and exit. */
+ * gout and gother have g_strides.  workspace: c2m_warp_bwd_workspace_bytes() bytes for the SAME
+ * flags, 256-byte aligned, contents undefined on entry and exit (the query is not told the layout and
+ * sizes for the larger of the channels-last and NCHW schemes). */
 C2M_API int c2m_warp_blend_bwd(const float* x, const float* flow, const float* mask, const float* other,
                        const float* gout, float* gx, float* gflow, float* gmask, float* gother,
                        int64_t N, int C, int H, int W, int64_t x_batch,
