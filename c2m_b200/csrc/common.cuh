@@ -226,8 +226,6 @@ __device__ __forceinline__ void prefetch_l2(const void* p, uint32_t bytes) {
 // streaming (evict-first) accesses for data touched exactly once
 __device__ __forceinline__ void st_stream(float* p, float v) { __stcs(p, v); }
 __device__ __forceinline__ void st_stream(float4* p, float4 v) { __stcs(p, v); }
-__device__ __forceinline__ float ld_stream(const float* p) { return __ldcs(p); }
-__device__ __forceinline__ float4 ld_stream(const float4* p) { return __ldcs(p); }
 
 // Read-only 128-bit load as a volatile asm statement: the compiler keeps a run of these together
 // (it otherwise interleaves loads with their first uses and leaves only two in flight), which is
@@ -301,26 +299,6 @@ __device__ __forceinline__ void tile_pipeline_init(TileSmem<TH, TW>& s, const CU
   }
   __syncthreads();
   if (threadIdx.x == 0 && first_tile < total) issue_tile<TH, TW, HAS_MASK>(s, tmf, tmm, first_tile, tiles_x, tiles_y, 0);
-}
-
-// Per-pixel geometry of one tile, computed once by a thread-per-pixel pass and then read
-// (broadcast) by the lanes that move a pixel's channels.
-template <int TP>
-struct TileGeo {
-  alignas(16) int4 off[TP];    // pixel offsets (y*W+x) of nw, ne, sw, se, clamped into the image
-  alignas(16) float4 w[TP];    // bilinear weights nw, ne, sw, se
-  alignas(16) float4 aux[TP];  // ax, ay, gmx, gmy (backward only)
-  float m[TP];                 // occlusion mask value (1 when there is no mask)
-  int ok[TP];                  // bit k set <=> corner k is inside the image; bit 4 <=> pixel inside the image
-};
-
-template <int TP>
-__device__ __forceinline__ void store_geo(TileGeo<TP>& tg, int t, const Geo& g, float m, int W, bool live) {
-  tg.off[t] = make_int4(g.y0 * W + g.x0, g.y0 * W + g.x1, g.y1 * W + g.x0, g.y1 * W + g.x1);
-  tg.w[t] = make_float4(g.wnw, g.wne, g.wsw, g.wse);
-  tg.aux[t] = make_float4(g.ax, g.ay, g.gmx, g.gmy);
-  tg.m[t] = m;
-  tg.ok[t] = live ? ((int)g.oknw | ((int)g.okne << 1) | ((int)g.oksw << 2) | ((int)g.okse << 3) | 16) : 0;
 }
 
 // ---------------------------------------------------------------------------------------------
