@@ -173,6 +173,27 @@ def test_kernel_variants_agree(dev, flags, layout):
     check(run_ours(x, flow, None, gout, flags=flags), run_ref(x, flow, None, gout))
 
 
+CL_SHAPES = [(3, 8, 19, 70), (2, 20, 24, 40), (2, 36, 9, 33), (1, 100, 16, 48), (2, 128, 16, 64), (1, 4, 40, 200)]
+
+
+@pytest.mark.parametrize("shape", CL_SHAPES, ids=[str(s) for s in CL_SHAPES])
+@pytest.mark.parametrize("amp", [3.0, 25.0], ids=["small_flow", "large_flow"])
+def test_channels_last_lane_mappings_and_options(dev, shape, amp):
+    """Every (lanes per pixel, groups per lane) instantiation of the channels-last kernels, ragged tile edges,
+    flows larger than a tile (candidate registration across many tiles), mask None and gradient subsets."""
+    N, C, H, W = shape
+    x, flow, mask, gout = make_inputs(dev, N, C, H, W, seed=sum(shape), amp=amp, noise=2.0)
+    x = x.contiguous(memory_format=torch.channels_last)
+    check(run_ours(x, flow, mask, gout), run_ref(x, flow, mask, gout))
+    check(run_ours(x, flow, None, gout), run_ref(x, flow, None, gout))
+    for need in [(True, False, False), (False, True, True), (True, True, False)]:
+        check(run_ours(x, flow, mask, gout, need=need), run_ref(x, flow, mask, gout, need=need))
+    d1 = run_ours(x, flow, mask, gout, deterministic=True)
+    d2 = run_ours(x, flow, mask, gout, deterministic=True)
+    assert torch.equal(d1[1][0], d2[1][0])
+    check(d1, run_ref(x, flow, mask, gout))
+
+
 @pytest.mark.parametrize("variant", range(0, 6))
 def test_nchw_tile_variants(dev, variant):
     x, flow, mask, gout = make_inputs(dev, 2, 16, 48, 96, seed=6)
