@@ -473,17 +473,16 @@ __device__ __forceinline__ void dot_finish(const DotRegs<NQ>& r, float& sa, floa
 
 //   LP  lanes per pixel (a warp moves 32/LP pixels side by side)
 //   QI  float4 groups per lane when C/4 == LP*QI exactly, 0 = run-time channel loop
-//   LOCAL   the contributor lists are built by the CTA itself in shared memory from the row segments that
-//           segbin_kernel registered as candidates for this destination tile (no global lists, no global
-//           atomics per contribution); otherwise they are read from the global lists bin_kernel wrote.
-//   DET     deterministic grad-input (local binning only): fixed-point integer accumulation
-template <int LP, int QI, bool DO_GX, bool DO_GF, bool HAS_MASK, bool USE_TMA, bool LOCAL, bool DET = false>
+// The contributor lists are built by the CTA itself in shared memory from the row segments that segbin_kernel
+// registered as candidates for this destination tile (no global lists, no global atomics per contribution).
+//   DET     deterministic grad-input: fixed-point integer accumulation
+template <int LP, int QI, bool DO_GX, bool DO_GF, bool HAS_MASK, bool USE_TMA, bool DET = false>
 __global__ void __launch_bounds__(256, 4) gather_nhwc_kernel(const __grid_constant__ BwdParams p,
                                                              const __grid_constant__ CUtensorMap tm_flow,
                                                              const __grid_constant__ CUtensorMap tm_mask) {
   constexpr int TH = 8, TW = 32;
   constexpr int G = 32 / LP;
-  constexpr int CAP = LOCAL ? kLocalCap : kListCap;  // entries per destination held in shared memory
+  constexpr int CAP = kLocalCap;  // entries per destination held in shared memory
   constexpr int NP = CAP / 2;                        // as int4 entry pairs
   __shared__ alignas(128) float s_flow[DO_GF ? 2 : 1][TH][TW];
   __shared__ alignas(128) float s_mask[TH][TW];
@@ -542,7 +541,7 @@ __global__ void __launch_bounds__(256, 4) gather_nhwc_kernel(const __grid_consta
       if (HAS_MASK) m = __ldg(p.mask + (int64_t)n * HW + pix);
     }
   }
-  if (LOCAL && DO_GX) {
+  if (DO_GX) {
     // ---- local binning: every warp walks candidate row segments (32 output pixels each), recomputes their
     // geometry and files the contributions that land inside this tile into the destination's list
     s_cnt[warp][lane] = 0;
@@ -627,30 +626,8 @@ __global__ void __launch_bounds__(256, 4) gather_nhwc_kernel(const __grid_consta
     if (DET) __threadfence();
     __syncthreads();
   }
-  if (DO_GX && live) {
-    const int self = (int)(((uint32_t)n * (uint32_t)HW + (uint32_t)pix) * (uint32_t)C4);  // a valid gout pixel for padding
-    if (LOCAL) {
-      // nothing to stage: the lists are already in shared memory (phase 1 clamps the count and ignores
-      // the slots past it)
-      if (DET && __ldcg(p.touched + (int64_t)n * HW + pix)) s_cnt[warp][lane] |= 0x40000000;
-    } else {  // global lists (issued before the TMA wait so the two overlap)
-      const int64_t ndest = (int64_t)HW * d.x_batch;
-      const int64_t D = (int64_t)n * HW + pix;
-      const int c = min(__ldg(p.cnt + D), kListCap);
-      const int4* ep = reinterpret_cast<const int4*>(p.entries) + D;
-      int4 e[NP];
-#pragma unroll
-      for (int k = 0; k < NP; ++k)
-        if (2 * k < c) e[k] = __ldg(ep + (int64_t)k * ndest);
-#pragma unroll
-      for (int k = 0; k < NP; ++k) {
-        if (2 * k >= c) { e[k].x = self; e[k].y = 0; }
-        if (2 * k + 1 >= c) { e[k].z = self; e[k].w = 0; }
-        if (k < 2 || 2 * k < c) s_ent[k][warp][lane] = e[k];
-      }
-      s_cnt[warp][lane] = c;
-    }
-  }
+  // (the lists stay where local binning put them: phase 1 clamps the count and ignores the slots past it)
+  if (DO_GX && DET && live && __ldcg(p.touched + (int64_t)n * HW + pix)) s_cnt[warp][lane] |= 0x40000000;
   if (DO_GF && USE_TMA) {
     mbar_wait(&bar, 0);
     fx = s_flow[0][warp][lane];
@@ -1019,14 +996,12 @@ size_t gather_workspace_bytes(int64_t N, int H, int W, int64_t x_batch) {
   return a > b ? a : b;
 }
 
-static bool use_local_binning();
-
 bool gather_supported(const BwdParams& p, Layout lx, Layout lg) {
   const Dims& d = p.d;
   if (d.flags & (C2M_FLAG_BWD_ATOMIC | C2M_FLAG_FORCE_GENERIC | C2M_FLAG_COORD_GRID | C2M_FLAG_TRUE_DIV | C2M_FLAG_NO_FMA))
     return false;
-  // deterministic grad-input: only the channels-last local-binning gather has an order-independent form
-  if ((d.flags & C2M_FLAG_DETERMINISTIC) && p.gx && !(lx == LAYOUT_NHWC && use_local_binning())) return false;
+  // deterministic grad-input: only the channels-last gather has an order-independent form
+  if ((d.flags & C2M_FLAG_DETERMINISTIC) && p.gx && lx != LAYOUT_NHWC) return false;
   if (p.other || p.gother) return false;
   if (lx != lg || lx == LAYOUT_OTHER) return false;
   if ((int64_t)d.N * d.H * d.W >= (1ll << 31) - 1) return false;
@@ -1041,7 +1016,7 @@ bool gather_supported(const BwdParams& p, Layout lx, Layout lg) {
   return true;
 }
 
-template <int LP, int QI, bool DO_GX, bool DO_GF, bool LOCAL, bool DET>
+template <int LP, int QI, bool DO_GX, bool DO_GF, bool DET>
 static void launch_gather_nhwc(BwdParams p, cudaStream_t st) {
   p.pf_tiles = prefetch_tiles(-1);  // measured: with four CTAs per SM resident the L2 prefetch gains nothing
   constexpr int TH = 8, TW = 32;
@@ -1051,7 +1026,7 @@ static void launch_gather_nhwc(BwdParams p, cudaStream_t st) {
   memset(&tm, 0, sizeof(tm));
   if (DO_GF) tm = make_tile_maps(d, p.flow, p.mask, TH, TW);
 #define C2M_LAUNCH(MASK, TMA) \
-  gather_nhwc_kernel<LP, QI, DO_GX, DO_GF, MASK, TMA, LOCAL, DET><<<tiles, TH * TW, 0, st>>>(p, tm.flow, tm.mask)
+  gather_nhwc_kernel<LP, QI, DO_GX, DO_GF, MASK, TMA, DET><<<tiles, TH * TW, 0, st>>>(p, tm.flow, tm.mask)
   if (p.mask) {
     if (tm.ok) C2M_LAUNCH(true, true); else C2M_LAUNCH(true, false);
   } else {
@@ -1061,23 +1036,21 @@ static void launch_gather_nhwc(BwdParams p, cudaStream_t st) {
   count_launch();
 }
 
-template <bool DO_GX, bool DO_GF, bool LOCAL, bool DET = false>
+template <bool DO_GX, bool DO_GF, bool DET = false>
 static void launch_gather_nhwc_lp(const BwdParams& p, cudaStream_t st) {
   const int C4 = p.d.C / 4;
   switch (C4) {  // two float4 groups per lane where C allows: half the per-pixel overhead of one
-    case 1: return launch_gather_nhwc<1, 1, DO_GX, DO_GF, LOCAL, DET>(p, st);
-    case 2: return launch_gather_nhwc<1, 2, DO_GX, DO_GF, LOCAL, DET>(p, st);
-    case 4: return launch_gather_nhwc<2, 2, DO_GX, DO_GF, LOCAL, DET>(p, st);
-    case 8: return launch_gather_nhwc<4, 2, DO_GX, DO_GF, LOCAL, DET>(p, st);
-    case 16: return launch_gather_nhwc<8, 2, DO_GX, DO_GF, LOCAL, DET>(p, st);
-    case 32: return launch_gather_nhwc<16, 2, DO_GX, DO_GF, LOCAL, DET>(p, st);
-    case 64: return launch_gather_nhwc<32, 2, DO_GX, DO_GF, LOCAL, DET>(p, st);
+    case 8: return launch_gather_nhwc<4, 2, DO_GX, DO_GF, DET>(p, st);    // C = 32
+    case 16: return launch_gather_nhwc<8, 2, DO_GX, DO_GF, DET>(p, st);   // C = 64
+    case 32: return launch_gather_nhwc<16, 2, DO_GX, DO_GF, DET>(p, st);  // C = 128
+    case 64: return launch_gather_nhwc<32, 2, DO_GX, DO_GF, DET>(p, st);  // C = 256
     default: break;
   }
-  if (C4 >= 24) return launch_gather_nhwc<32, 0, DO_GX, DO_GF, LOCAL, DET>(p, st);
-  if (C4 >= 12) return launch_gather_nhwc<16, 0, DO_GX, DO_GF, LOCAL, DET>(p, st);
-  if (C4 >= 6) return launch_gather_nhwc<8, 0, DO_GX, DO_GF, LOCAL, DET>(p, st);
-  return launch_gather_nhwc<4, 0, DO_GX, DO_GF, LOCAL, DET>(p, st);
+  // any other channel count: run-time channel loop
+  if (C4 >= 24) return launch_gather_nhwc<32, 0, DO_GX, DO_GF, DET>(p, st);
+  if (C4 >= 12) return launch_gather_nhwc<16, 0, DO_GX, DO_GF, DET>(p, st);
+  if (C4 >= 6) return launch_gather_nhwc<8, 0, DO_GX, DO_GF, DET>(p, st);
+  return launch_gather_nhwc<4, 0, DO_GX, DO_GF, DET>(p, st);
 }
 
 template <bool DO_GX, bool DO_GF, bool REPEAT>
@@ -1132,21 +1105,13 @@ __global__ void __launch_bounds__(256) absmax_flat_kernel(const float* __restric
 
 __global__ void set_bits_kernel(unsigned* p, unsigned v) { *p = v; }
 
-static bool use_local_binning() {
-  static const bool v = [] {
-    const char* e = getenv("C2M_WARP_BWD_LISTS");  // tuning hook: 1 = global contributor lists also for channels-last
-    return !(e && *e && atoi(e) != 0);
-  }();
-  return v;
-}
-
 int launch_bwd_gather(const BwdParams& pin, Layout lx, void* workspace, size_t workspace_bytes, cudaStream_t st) {
   BwdParams p = pin;
   const Dims& d = p.d;
   const bool need_gf = p.gflow || p.gmask;
   const bool repeat = d.x_batch != d.N;
   const bool fuse = p.gx && need_gf && !repeat;
-  const bool local = lx == LAYOUT_NHWC && use_local_binning();
+  const bool local = lx == LAYOUT_NHWC;  // channels-last: local binning; NCHW kernels: global contributor lists
   p.n0 = 0;
   p.nframes = d.N;
   p.key_mul = lx == LAYOUT_NHWC ? d.C / 4 : 1;  // channels-last lists address gout in 16-byte units
@@ -1207,27 +1172,18 @@ int launch_bwd_gather(const BwdParams& pin, Layout lx, void* workspace, size_t w
   if (lx == LAYOUT_NHWC) {
     BwdParams q = p;
     q.nframes = d.x_batch;  // a grad-input-only pass walks the images of x
-    if (local && det) {
-      if (fuse) {
-        launch_gather_nhwc_lp<true, true, true, true>(p, st);
-      } else {
-        launch_gather_nhwc_lp<true, false, true, true>(q, st);
-        if (need_gf) launch_gather_nhwc_lp<false, true, false>(p, st);
-      }
-    } else if (local) {
+    if (det) {
       if (fuse) {
         launch_gather_nhwc_lp<true, true, true>(p, st);
       } else {
-        if (p.gx) launch_gather_nhwc_lp<true, false, true>(q, st);
-        if (need_gf) launch_gather_nhwc_lp<false, true, false>(p, st);
+        launch_gather_nhwc_lp<true, false, true>(q, st);
+        if (need_gf) launch_gather_nhwc_lp<false, true>(p, st);
       }
+    } else if (fuse) {
+      launch_gather_nhwc_lp<true, true>(p, st);
     } else {
-      if (fuse) {
-        launch_gather_nhwc_lp<true, true, false>(p, st);
-      } else {
-        if (p.gx) launch_gather_nhwc_lp<true, false, false>(q, st);
-        if (need_gf) launch_gather_nhwc_lp<false, true, false>(p, st);
-      }
+      if (p.gx) launch_gather_nhwc_lp<true, false>(q, st);
+      if (need_gf) launch_gather_nhwc_lp<false, true>(p, st);
     }
   } else if (fuse) {
     launch_gather_nchw<true, true, false>(p, st);
