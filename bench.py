@@ -171,13 +171,11 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
 def run_ours(args):
-    # rank 0 prints exactly one line on stdout: NCCL's own messages (version banner) go to stderr
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import c2m_b200
     from c2m_b200 import _lib
     from c2m_b200 import dist as cdist
@@ -404,11 +402,42 @@ def run_ours(args):
             "e2e": e2e,
             "gpu_launches": launches, "clocks": clk.summary(),
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
     return 0
+
+
+class _QuietStdout:
+    """Everything any library writes to stdout (fd 1) while the benchmark runs -- NCCL's version banner, for one
+    -- is sent to stderr; only the result line goes to the real stdout."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, text):
+        sys.stdout.flush()
+        os.write(self.saved, (text + "\n").encode())
+
+    def __exit__(self, *a):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
+_OUT = None
+
+
+def emit(line):
+    text = json.dumps(line)
+    if _OUT is not None:
+        _OUT.emit(text)
+    else:
+        print(text, flush=True)
 
 
 def main():
@@ -431,9 +460,13 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--e2e-chunks", type=int, default=8)
     args = ap.parse_args()
-    if args.impl == "reference":
-        return run_reference(args)
-    return run_ours(args)
+    global _OUT
+    with _QuietStdout() as q:
+        _OUT = q
+        try:
+            return run_reference(args) if args.impl == "reference" else run_ours(args)
+        finally:
+            _OUT = None
 
 
 if __name__ == "__main__":

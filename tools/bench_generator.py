@@ -83,7 +83,8 @@ def main():
     ap.add_argument("--dataset", default="cityscapes")
     ap.add_argument("--no-channels-last", dest="channels_last", action="store_false")
     args = ap.parse_args()
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    saved_stdout = os.dup(1)  # library chatter on stdout (NCCL banner) goes to stderr; the result line to stdout
+    os.dup2(2, 1)
     rank, local_rank, world = cdist.init()
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -96,7 +97,8 @@ def main():
                 "results": res}
         if len(res) == 2:
             line["step_speedup_fused_vs_torch"] = res["torch"]["ms_per_step"] / res["fused"]["ms_per_step"]
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(saved_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
