@@ -36,6 +36,8 @@ SYMBOLS = (
     "c2m_warp_launch_count",
     "c2m_occlusion_map",
     "c2m_occlusion_map_workspace_bytes",
+    "c2m_warp_profile",
+    "c2m_warp_profile_last_ms",
 )
 
 _lock = threading.Lock()
@@ -86,6 +88,10 @@ def load(build_if_missing: bool = False) -> ctypes.CDLL:
         lib.c2m_warp_bwd_workspace_bytes.argtypes = [_i64, _int, _int, _int, _i64, _int, _int]
         lib.c2m_base_grid.restype = _int
         lib.c2m_base_grid.argtypes = [_ptr, _i64, _int, _int, _ptr]
+        lib.c2m_warp_profile.restype = _int
+        lib.c2m_warp_profile.argtypes = [_int]
+        lib.c2m_warp_profile_last_ms.restype = ctypes.c_float
+        lib.c2m_warp_profile_last_ms.argtypes = []
         lib.c2m_occlusion_map_workspace_bytes.restype = ctypes.c_size_t
         lib.c2m_occlusion_map_workspace_bytes.argtypes = [_i64, _int, _int]
         lib.c2m_occlusion_map.restype = _int
@@ -137,6 +143,15 @@ def occlusion_map(in_ptr, out_ptr, N, H, W, flags, ws_ptr, ws_bytes, stream) -> 
 
 def occlusion_map_workspace_bytes(N, H, W) -> int:
     return int(load().c2m_occlusion_map_workspace_bytes(N, H, W))
+
+
+def profile(enable: bool) -> None:
+    """Measurement hook: bracket the dominant kernel of every call of this thread with CUDA events."""
+    _check(load().c2m_warp_profile(int(bool(enable))), "c2m_warp_profile")
+
+
+def profile_last_ms() -> float:
+    return float(load().c2m_warp_profile_last_ms())
 
 
 def launch_count() -> int:

@@ -23,6 +23,25 @@ void set_error(const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
+struct ProfileState {
+  bool on = false, valid = false;
+  cudaEvent_t a = nullptr, b = nullptr;
+};
+// process-wide on purpose: autograd runs the backward call on its own thread, the reader is the main thread
+static ProfileState g_prof;
+static std::mutex g_prof_mu;
+
+void profile_begin(cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (!g_prof.on) return;
+  g_prof.valid = cudaEventRecord(g_prof.a, st) == cudaSuccess;
+}
+void profile_end(cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (!g_prof.on || !g_prof.valid) return;
+  g_prof.valid = cudaEventRecord(g_prof.b, st) == cudaSuccess;
+}
+
 int sm_count() {
   static thread_local int cached_dev = -1, cached = 148;
   int dev = 0;
@@ -166,6 +185,31 @@ extern "C" {
 int c2m_warp_version(void) { return C2M_WARP_VERSION; }
 const char* c2m_warp_last_error(void) { return g_err; }
 uint64_t c2m_warp_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int c2m_warp_profile(int enable) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (enable && !g_prof.a) {
+    if (cudaEventCreate(&g_prof.a) != cudaSuccess || cudaEventCreate(&g_prof.b) != cudaSuccess) {
+      set_error("c2m_warp_profile: cudaEventCreate failed");
+      (void)cudaGetLastError();
+      return C2M_ERR_CUDA;
+    }
+  }
+  g_prof.on = enable != 0;
+  g_prof.valid = false;
+  return C2M_OK;
+}
+
+float c2m_warp_profile_last_ms(void) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (!g_prof.a || !g_prof.valid) return -1.f;
+  float ms = -1.f;
+  if (cudaEventSynchronize(g_prof.b) != cudaSuccess || cudaEventElapsedTime(&ms, g_prof.a, g_prof.b) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return -1.f;
+  }
+  return ms;
+}
 
 int c2m_warp_blend_fwd(const float* x, const float* flow, const float* mask, const float* other, float* out,
                        int64_t N, int C, int H, int W, int64_t x_batch, const int64_t x_strides[4],

@@ -317,6 +317,9 @@ struct ListEntry {
 };
 
 void set_error(const char* fmt, ...);
+// measurement hook (c2m_warp_profile): record the thread's event pair around the dominant kernel of a call
+void profile_begin(cudaStream_t st);
+void profile_end(cudaStream_t st);
 void count_launch(int n = 1);
 int sm_count();
 // L2 prefetch distance of the channels-last kernels, in tiles (< 0: off); the environment variable

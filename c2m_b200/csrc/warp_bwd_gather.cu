@@ -1169,6 +1169,7 @@ int launch_bwd_gather(const BwdParams& pin, Layout lx, void* workspace, size_t w
     bin_kernel<<<(unsigned)((total + kBinPixelsPerBlock - 1) / kBinPixelsPerBlock), 256, 0, st>>>(p);
     count_launch();
   }
+  profile_begin(st);  // the gather kernel(s): the dominant part of the backward
   if (lx == LAYOUT_NHWC) {
     BwdParams q = p;
     q.nframes = d.x_batch;  // a grad-input-only pass walks the images of x
@@ -1194,6 +1195,7 @@ int launch_bwd_gather(const BwdParams& pin, Layout lx, void* workspace, size_t w
     }
     if (need_gf) launch_gather_nchw<false, true, false>(p, st);
   }
+  profile_end(st);
   if (p.gx && !(local && det)) {
     const int grid = sm_count() * 8;
     if (lx == LAYOUT_NHWC)  // gather_supported() has checked C % 4 and the 16-byte alignment

@@ -336,7 +336,16 @@ static int launch_nhwc(const FwdParams& p, cudaStream_t st) {
   return launch_nhwc_t<4, 0>(p, st);
 }
 
+static int launch_fwd_impl(const FwdParams& p, Layout lx, Layout lo, cudaStream_t st);
+
 int launch_fwd(const FwdParams& p, Layout lx, Layout lo, cudaStream_t st) {
+  profile_begin(st);  // the forward is a single kernel
+  const int rc = launch_fwd_impl(p, lx, lo, st);
+  profile_end(st);
+  return rc;
+}
+
+static int launch_fwd_impl(const FwdParams& p, Layout lx, Layout lo, cudaStream_t st) {
   const Dims& d = p.d;
   const bool generic = (d.flags & (C2M_FLAG_FORCE_GENERIC | C2M_FLAG_COORD_GRID | C2M_FLAG_TRUE_DIV | C2M_FLAG_NO_FMA)) ||
                        p.other != nullptr || lx != lo ||

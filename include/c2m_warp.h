@@ -114,6 +114,14 @@ C2M_API size_t c2m_occlusion_map_workspace_bytes(int64_t N, int H, int W);
 C2M_API int c2m_occlusion_map(const float* in, float* out, int64_t N, int H, int W, int flags, void* workspace,
                               size_t workspace_bytes, void* cuda_stream);
 
+/* Measurement hook (process wide, off by default, not meant for concurrent callers).  While enabled, every
+ * forward / backward call brackets its
+ * dominant kernel -- the fused forward kernel; the gather kernel of the backward -- with a pair of CUDA events on the
+ * call's stream.  c2m_warp_profile_last_ms() waits for the stop event of the most recent call and
+ * returns that kernel's duration in milliseconds (< 0: nothing recorded).  Used by bench.py for `roofline`. */
+C2M_API int c2m_warp_profile(int enable);
+C2M_API float c2m_warp_profile_last_ms(void);
+
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
 C2M_API uint64_t c2m_warp_launch_count(void);
 
