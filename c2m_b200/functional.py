@@ -69,7 +69,10 @@ def _check_inputs(x, flow, mask, other):
 class WarpBlendFunction(torch.autograd.Function):
     """out = mask * bilinear_border_warp(x, flow) [+ (1 - mask) * other]."""
 
+    # under autocast the op runs in float32 with its inputs cast up, the convention of the reference's own
+    # native warp (src/modules/third_party/resample2d/resample2d.py:55-57: autocast(False) + .float())
     @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(ctx, x, flow, mask, other, padding, deterministic, flags):
         _check_inputs(x, flow, mask, other)
         nhwc = _is_nhwc_dense(x)
@@ -91,6 +94,7 @@ class WarpBlendFunction(torch.autograd.Function):
 
     @staticmethod
     @once_differentiable
+    @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, gout):
         x, flow, mask, other = ctx.saved_tensors
         padding, deterministic, flags, nhwc = ctx.cfg

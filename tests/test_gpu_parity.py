@@ -353,6 +353,21 @@ def test_non_default_stream_and_noncontiguous_inputs(dev):
     check(ours, run_ref(xs.contiguous(), flow, mask, gout))
 
 
+def test_runs_in_float32_under_autocast(dev):
+    x, flow, mask, gout = make_inputs(dev, 2, 8, 16, 32, seed=31)
+    ref = run_ours(x, flow, mask, gout)
+    xa = x.clone().requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out = c2m_b200.warp_blend(xa.half(), flow.half(), mask)  # half inputs are cast up, not rejected
+        assert out.dtype == torch.float32
+    out2 = c2m_b200.warp_blend(x.half().float(), flow.half().float(), mask)
+    assert torch.equal(out, out2)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        o = c2m_b200.warp_blend(xa, flow, mask)
+        g = torch.autograd.grad(o, [xa], gout)[0]
+    assert rel(o, ref[0]) <= FWD_TOL and rel(g, ref[1][0]) <= GRAD_TOL
+
+
 def test_errors_are_raised_not_swallowed(dev):
     x, flow, mask, gout = make_inputs(dev, 2, 4, 8, 8, seed=15)
     with pytest.raises(TypeError):
