@@ -6,6 +6,7 @@ gets an exception -- never a silent PyTorch/CPU path.
 from __future__ import annotations
 
 import ctypes
+import functools
 import os
 import threading
 
@@ -106,8 +107,14 @@ def _check(rc: int, what: str) -> None:
         raise C2MWarpError(f"{what} failed (code {rc}): {msg}")
 
 
+@functools.lru_cache(maxsize=256)
+def _strides_cached(s):
+    return _Strides(*s)
+
+
 def strides4(s) -> "_Strides":
-    return _Strides(*[int(v) for v in s])
+    """ctypes int64[4] for a stride tuple (cached: the same few layouts come back on every call)."""
+    return _strides_cached(tuple(int(v) for v in s))
 
 
 def warp_blend_fwd(x_ptr, flow_ptr, mask_ptr, other_ptr, out_ptr, N, C, H, W, x_batch, x_strides, out_strides,

@@ -30,6 +30,22 @@ def _ptr(t):
     return None if t is None else t.data_ptr()
 
 
+class _on_device:
+    """`with torch.cuda.device(dev)` only when `dev` is not already current (the switch costs ~10 us of host time
+    per call, which is most of what the small pyramid levels spend)."""
+
+    def __init__(self, dev):
+        self.ctx = None if dev.index is None or dev.index == torch.cuda.current_device() else torch.cuda.device(dev)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *a):
+        if self.ctx is not None:
+            self.ctx.__exit__(*a)
+
+
 def _is_nhwc_dense(t: torch.Tensor) -> bool:
     return (t.dim() == 4 and not t.is_contiguous() and t.is_contiguous(memory_format=torch.channels_last))
 
@@ -84,7 +100,7 @@ class WarpBlendFunction(torch.autograd.Function):
         B, C = x.shape[0], x.shape[1]
         out = torch.empty((N, C, H, W), dtype=x.dtype, device=x.device,
                           memory_format=torch.channels_last if nhwc else torch.contiguous_format)
-        with torch.cuda.device(x.device):
+        with _on_device(x.device):
             stream = torch.cuda.current_stream().cuda_stream
             _lib.warp_blend_fwd(_ptr(x), _ptr(flow), _ptr(mask), _ptr(other), _ptr(out), N, C, H, W, B,
                                 x.stride(), out.stride(), padding, flags, stream)
@@ -114,7 +130,7 @@ class WarpBlendFunction(torch.autograd.Function):
             # NCHW tensors: the library stages them through channels-last copies in the workspace and runs
             # the channels-last kernels (about twice as fast as gathering 4-byte elements at NCHW strides)
             flags |= _lib.FLAG_STAGE_NHWC
-        with torch.cuda.device(x.device):
+        with _on_device(x.device):
             ws_bytes = _lib.bwd_workspace_bytes(N, C, H, W, B, need_x, flags)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
             stream = torch.cuda.current_stream().cuda_stream
