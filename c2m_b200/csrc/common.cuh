@@ -74,6 +74,9 @@ struct BwdParams {
                             // computed once by segbin_kernel and reused by every tile that bins the pixel
   int key_mul;              // list entries name their source as pixel index * key_mul
   int pf_tiles;             // channels-last: L2 prefetch distance in tiles (< 0: off)
+  int64_t ovf_stride;       // channel-sliced gather: slice s flags its own list overflows in ovf[(s + 1) * ovf_stride + pixel]
+                            // and lists them as pixel | (s + 1) << 24 (tag 0: all channels, from segbin_kernel)
+  float* gpart;             // channel-sliced gather (small levels): [slices][gflow N*2*HW | gmask N*HW] partial sums
 };
 
 // Per-pixel sampling geometry, shared by forward and backward.
@@ -307,6 +310,8 @@ __device__ __forceinline__ void tile_pipeline_init(TileSmem<TH, TW>& s, const CU
 enum Layout { LAYOUT_NCHW = 0, LAYOUT_NHWC = 1, LAYOUT_OTHER = 2 };
 
 // Gather-form backward: contributor lists (one per destination pixel of grad-input)
+constexpr int kSplitTiles = 592;  // fewer tiles than this (4 per SM): slice the channels over blockIdx.y
+constexpr int kSplitMax = 8;
 constexpr int kListCap = 8;   // global lists (NCHW path): in-line entries per destination; the tail goes through atomics
 constexpr int kLocalCap = 12; // channels-last local binning: entries per destination in shared memory
 constexpr int kCandPerFrame = 96;  // candidate row segments a destination tile can register per source frame

@@ -211,9 +211,11 @@ __global__ void __launch_bounds__(256, 6) fwd_nhwc_kernel(const __grid_constant_
   __syncwarp();
   const int lq = lane % LP, grp = lane / LP;
   const int npx = min(TW, d.W - bx * TW);  // live pixels of this row segment (warp-uniform)
-  const char* xl = reinterpret_cast<const char*>(p.x) + (int64_t)(n % d.x_batch) * HW * pxb + lq * 16;
-  char* ol = reinterpret_cast<char*>(p.out) + ((int64_t)n * HW + (int64_t)i * d.W + bx * TW + grp) * pxb + lq * 16;
-  const int C4 = d.C >> 2;
+  // blockIdx.y: channel slice of p.cchunk channels (small levels only: more CTAs than tiles)
+  const int C4 = p.cchunk >> 2;
+  const uint32_t cb0 = blockIdx.y * (uint32_t)p.cchunk * 4u + lq * 16;
+  const char* xl = reinterpret_cast<const char*>(p.x) + (int64_t)(n % d.x_batch) * HW * pxb + cb0;
+  char* ol = reinterpret_cast<char*>(p.out) + ((int64_t)n * HW + (int64_t)i * d.W + bx * TW + grp) * pxb + cb0;
   const int nq = QI > 0 ? QI : (C4 - lq + LP - 1) / LP;  // float4 groups of this lane
 #pragma unroll 1
   for (int s = 0; s < npx; s += G) {
@@ -305,7 +307,8 @@ static int launch_nhwc_t(FwdParams p, cudaStream_t st) {
   const Dims& d = p.d;
   const int tiles = d.N * ((d.H + TH - 1) / TH) * ((d.W + TW - 1) / TW);
   const TileMaps tm = make_tile_maps(d, p.flow, p.mask, TH, TW);
-#define C2M_LAUNCH(MASK, TMA) fwd_nhwc_kernel<LP, QI, MASK, TMA><<<tiles, TH * TW, 0, st>>>(p, tm.flow, tm.mask)
+#define C2M_LAUNCH(MASK, TMA) \
+  fwd_nhwc_kernel<LP, QI, MASK, TMA><<<dim3(tiles, d.C / p.cchunk), TH * TW, 0, st>>>(p, tm.flow, tm.mask)
   if (p.mask) {
     if (tm.ok) C2M_LAUNCH(true, true); else C2M_LAUNCH(true, false);
   } else {
@@ -317,8 +320,14 @@ static int launch_nhwc_t(FwdParams p, cudaStream_t st) {
 }
 
 // C/4 float4 groups per pixel -> (lanes per pixel, groups per lane)
-static int launch_nhwc(const FwdParams& p, cudaStream_t st) {
-  const int C4 = p.d.C / 4;
+static int launch_nhwc(FwdParams p, cudaStream_t st) {
+  // small pyramid levels have fewer tiles than the machine has CTA slots: slice the channels over
+  // blockIdx.y (each slice recomputes the tile geometry; slices stay whole 256-byte rows)
+  const Dims& d = p.d;
+  const int tiles = d.N * ((d.H + 7) / 8) * ((d.W + 31) / 32);
+  int C4 = d.C / 4;
+  while (tiles * (d.C / 4 / C4) < sm_count() * 6 && C4 % 2 == 0 && C4 / 2 >= 16) C4 /= 2;
+  p.cchunk = C4 * 4;
   switch (C4) {
     case 1: return launch_nhwc_t<1, 1>(p, st);
     case 2: return launch_nhwc_t<2, 1>(p, st);

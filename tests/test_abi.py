@@ -82,27 +82,45 @@ def test_argument_validation_happens_before_any_device_work():
 
 
 def test_workspace_size_contract():
-    # default (gather-form) backward: per destination pixel a 4 B counter (+ the overflow-list length and
-    # one per-frame "tiles binned" counter behind the counters) and 8 in-line (src, w) entries; per output
-    # pixel a 1 B overflow flag and a 4 B overflow-list slot; each block rounded up to 256 B
+    # default (gather-form) backward: the larger of the two schemes (the call is not told the layout).
+    #  NCHW global lists: per destination pixel a 4 B counter (+ the overflow-list length and one per-frame
+    #  "tiles binned" counter behind the counters) and 8 in-line (src, w) entries; per output pixel a 1 B
+    #  overflow flag and a 4 B overflow-list slot; each block rounded up to 256 B.
+    #  channels-last local binning: tile counters, overflow flags, candidate segments (8 B each, 96 per tile and
+    #  source frame), overflow list, 16 B pixel records; levels with fewer than 592 tiles (4 per SM) also get room
+    #  for a channel-sliced gather: 1 + 8 flag arrays / list segments and 8 slices of grad-flow / grad-mask partials.
     up = lambda v: (v + 255) // 256 * 256  # noqa: E731
-    npix = 4 * 16 * 32
-    assert _lib.bwd_workspace_bytes(4, 8, 16, 32, 4, True, 0) == (
-        256 + up(4 * (npix + 1 + 4)) + up(64 * npix) + up(npix) + up(4 * npix))
+
+    def global_lists(N, H, W, B):
+        npd, npo = B * H * W, N * H * W
+        return up(4 * (npd + 1 + 4)) + up(64 * npd) + up(npo) + up(4 * npo)
+
+    def local(N, C, H, W, B, det=False):
+        tiles_per = ((H + 7) // 8) * ((W + 31) // 32)
+        ntile, npo, npd = B * tiles_per, N * H * W, B * H * W
+        cap = min(256, 96 * (N // B))
+        small = N * tiles_per < 592
+        nov = 9 if small else 1
+        v = up(4 * (ntile + 1)) + nov * up(npo) + up(8 * ntile * cap) + up(4 * nov * npo) + up(16 * npo)
+        if small:
+            v += up(8 * 3 * npo * 4)
+        if det:  # + scale bits, touched flags and the int64 overflow rows
+            v += 256 + up(npd) + up(8 * npd * C)
+        return v
+
+    for (N, C, H, W, B) in [(4, 8, 16, 32, 4), (40, 64, 256, 512, 40), (10, 8, 16, 32, 2)]:
+        assert _lib.bwd_workspace_bytes(N, C, H, W, B, True, 0) == 256 + max(global_lists(N, H, W, B),
+                                                                            local(N, C, H, W, B))
     assert _lib.bwd_workspace_bytes(4, 8, 16, 32, 4, True, _lib.FLAG_BWD_ATOMIC) == 256
     # deterministic: the larger of (a) one int64 per grad-input element (generic fixed-point scatter) and
-    # (b) the channels-last gather's bookkeeping (tile counters, overflow flags, candidate segments (8 B each, 96 per tile and
-    # source frame), overflow list, 16 B pixel records) + scale bits, touched flags and the int64 overflow rows
-    def local_det(N, C, H, W, B):
-        ntile, npo, npd = B * ((H + 7) // 8) * ((W + 31) // 32), N * H * W, B * H * W
-        cap = min(256, 96 * (N // B))
-        return (up(4 * (ntile + 1)) + up(npo) + up(8 * ntile * cap) + up(4 * npo) + up(16 * npo)
-                + 256 + up(npd) + up(8 * npd * C))
+    # (b) the channels-last gather's bookkeeping
     det = _lib.bwd_workspace_bytes(4, 8, 16, 32, 4, True, _lib.FLAG_DETERMINISTIC)
-    assert det == 256 + max(4 * 8 * 16 * 32 * 8, local_det(4, 8, 16, 32, 4))
+    assert det == 256 + max(4 * 8 * 16 * 32 * 8, local(4, 8, 16, 32, 4, True))
     # repeat: gx only has x_batch images
     assert _lib.bwd_workspace_bytes(10, 8, 16, 32, 2, True, _lib.FLAG_DETERMINISTIC) == (
-        256 + max(2 * 8 * 16 * 32 * 8, local_det(10, 8, 16, 32, 2)))
+        256 + max(2 * 8 * 16 * 32 * 8, local(10, 8, 16, 32, 2, True)))
+    assert _lib.bwd_workspace_bytes(40, 64, 256, 512, 40, True, _lib.FLAG_DETERMINISTIC) == (
+        256 + max(40 * 64 * 256 * 512 * 8, local(40, 64, 256, 512, 40, True)))
     assert _lib.bwd_workspace_bytes(4, 8, 16, 32, 4, False, _lib.FLAG_DETERMINISTIC) == 256
 
 

@@ -194,6 +194,28 @@ def test_channels_last_lane_mappings_and_options(dev, shape, amp):
     check(d1, run_ref(x, flow, mask, gout))
 
 
+SLICED = [(4, 128, 16, 32, None), (2, 256, 8, 16, None), (3, 512, 8, 16, None), (6, 256, 16, 32, 2), (2, 192, 12, 40, None)]
+
+
+@pytest.mark.parametrize("cfg", SLICED, ids=[str(s) for s in SLICED])
+def test_channel_sliced_small_levels(dev, cfg):
+    """Small pyramid levels with many channels: the channels-last kernels slice the channels over blockIdx.y
+    (2, 4 and 8 slices here); steep flows make destination lists overflow inside the slices (per-slice overflow
+    records), grad-flow / grad-mask are the sum of the slices' partial sums; also with the frame repeat."""
+    N, C, H, W, B = cfg
+    for amp, noise in [(2.0, 0.5), (8.0, 1.0)]:
+        x, flow, mask, gout = make_inputs(dev, N, C, H, W, seed=N + C + H, amp=amp, noise=noise, B=B)
+        x = x.contiguous(memory_format=torch.channels_last)
+        gout = gout.contiguous(memory_format=torch.channels_last)
+        check(run_ours(x, flow, mask, gout), run_ref(x, flow, mask, gout, B=B))
+        check(run_ours(x, flow, None, gout), run_ref(x, flow, None, gout, B=B))
+        for need in [(True, False, False), (False, True, True)]:
+            check(run_ours(x, flow, mask, gout, need=need), run_ref(x, flow, mask, gout, need=need, B=B))
+        d1 = run_ours(x, flow, mask, gout, deterministic=True)
+        assert torch.equal(d1[1][0], run_ours(x, flow, mask, gout, deterministic=True)[1][0])
+        check(d1, run_ref(x, flow, mask, gout, B=B))
+
+
 @pytest.mark.parametrize("variant", range(0, 6))
 def test_nchw_tile_variants(dev, variant):
     x, flow, mask, gout = make_inputs(dev, 2, 16, 48, 96, seed=6)

@@ -35,7 +35,7 @@ def main(iters, seed):
     for it in range(iters):
         torch.manual_seed(seed * 100003 + it)
         H, W = rnd.randint(2, 70), rnd.randint(2, 150)
-        C = rnd.choice([4, 8, 12, 16, 20, 32, 36, 64, 100, 128, 3, 5])
+        C = rnd.choice([4, 8, 12, 16, 20, 32, 36, 64, 100, 128, 192, 256, 512, 3, 5])
         T = rnd.choice([1, 1, 1, 2, 5])
         B = rnd.randint(1, 3)
         N = B * T
