@@ -54,6 +54,27 @@ int sm_count() {
   return cached;
 }
 
+// Channels-last kernels slice the channels over blockIdx.y while a level has fewer tiles than this
+// (C2M_WARP_SPLIT_TILES overrides; 0 switches the slicing off).
+int split_tiles() {
+  static const int v = [] {
+    const char* e = getenv("C2M_WARP_SPLIT_TILES");
+    return e && *e ? atoi(e) : kSplitTiles;
+  }();
+  return v;
+}
+
+int channel_slices(int64_t N, int C, int H, int W) {
+  if ((C & 3) || N * H * W >= (1ll << 24)) return 1;  // (slice tags share a 32-bit word with the pixel index)
+  const int64_t tiles = N * ((H + 7) / 8) * ((W + 31) / 32);
+  int C4 = C / 4, s = 1;
+  while (tiles * s < split_tiles() && s < kSplitMax && C4 % 2 == 0 && C4 / 2 >= 16) {
+    C4 /= 2;
+    s *= 2;
+  }
+  return s;
+}
+
 int prefetch_tiles(int dflt) {
   static const int v = [] {
     const char* e = getenv("C2M_WARP_PREFETCH_TILES");

@@ -310,7 +310,7 @@ __device__ __forceinline__ void tile_pipeline_init(TileSmem<TH, TW>& s, const CU
 enum Layout { LAYOUT_NCHW = 0, LAYOUT_NHWC = 1, LAYOUT_OTHER = 2 };
 
 // Gather-form backward: contributor lists (one per destination pixel of grad-input)
-constexpr int kSplitTiles = 592;  // fewer tiles than this (4 per SM): slice the channels over blockIdx.y
+constexpr int kSplitTiles = 1184;  // fewer tiles than this (8 per SM): slice the channels over blockIdx.y
 constexpr int kSplitMax = 8;
 constexpr int kListCap = 8;   // global lists (NCHW path): in-line entries per destination; the tail goes through atomics
 constexpr int kLocalCap = 12; // channels-last local binning: entries per destination in shared memory
@@ -330,6 +330,8 @@ int sm_count();
 // L2 prefetch distance of the channels-last kernels, in tiles (< 0: off); the environment variable
 // C2M_WARP_PREFETCH_TILES overrides the kernel's default (tuning hook)
 int prefetch_tiles(int dflt);
+// number of blockIdx.y channel slices the channels-last kernels use for a level (1: none)
+int channel_slices(int64_t N, int C, int H, int W);
 // Number of CTAs of `kernel` (static shared memory only) that are resident on the whole device at once:
 // the grid size of a persistent launch.
 int resident_ctas(const void* kernel, int threads);

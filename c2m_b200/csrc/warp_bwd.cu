@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(256) fix2float_kernel(const long long* acc, fl
 }
 
 // ---------------------------------------------------------------------------------------------
-size_t gather_workspace_bytes(int64_t N, int H, int W, int64_t x_batch);
+size_t gather_workspace_bytes(int64_t N, int C, int H, int W, int64_t x_batch);
 size_t local_det_workspace_bytes(int64_t N, int C, int H, int W, int64_t x_batch);
 bool gather_supported(const BwdParams& p, Layout lx, Layout lg);
 int launch_bwd_gather(const BwdParams& pin, Layout lx, void* workspace, size_t workspace_bytes, cudaStream_t st);
@@ -147,7 +147,7 @@ size_t bwd_workspace_bytes(int64_t N, int C, int H, int W, int64_t x_batch, int 
     b += a > l ? a : l;
     if (flags & C2M_FLAG_STAGE_NHWC) b += stage_bytes(N, C, H, W, xb);
   } else if (!(flags & (C2M_FLAG_BWD_ATOMIC | C2M_FLAG_FORCE_GENERIC | C2M_FLAG_COORD_GRID))) {
-    b += gather_workspace_bytes(N, H, W, xb);  // contributor lists / candidate lists
+    b += gather_workspace_bytes(N, C, H, W, xb);  // contributor lists / candidate lists
     if (flags & C2M_FLAG_STAGE_NHWC) b += stage_bytes(N, C, H, W, xb);
   }
   return b;

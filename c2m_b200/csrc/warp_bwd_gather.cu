@@ -963,6 +963,7 @@ struct LocalWs {
   int* ovf_list;
   int4* pixrec;
   float* gpart;
+  int slices;
   size_t ovf_stride;
   int cand_cap;
   size_t clear_bytes;
@@ -974,12 +975,13 @@ struct LocalWs {
   size_t det_clear_bytes;  // [maxbits | touched | acc64]
 };
 
-static LocalWs carve_local(void* base, int64_t N, int H, int W, int64_t x_batch, int C = 0, bool det = false) {
+static LocalWs carve_local(void* base, int64_t N, int H, int W, int64_t x_batch, int C, bool det = false) {
   const size_t ntile = (size_t)x_batch * ((H + 7) / 8) * ((W + 31) / 32), npix_o = (size_t)N * H * W;
   // small level (fewer tiles than CTA slots): room for a channel-sliced gather -- per-slice overflow flags
   // and list entries, per-slice grad-flow / grad-mask partial sums
-  const bool small = (size_t)N * ((H + 7) / 8) * ((W + 31) / 32) < (size_t)kSplitTiles;
-  const size_t nov = small ? 1 + kSplitMax : 1;
+  const int slices = det ? 1 : channel_slices(N, C, H, W);
+  const bool small = slices > 1;
+  const size_t nov = small ? 1 + slices : 1;
   LocalWs w;
   int64_t cap = (int64_t)kCandPerFrame * (x_batch > 0 ? N / x_batch : 1);
   w.cand_cap = (int)(cap > kCandMax ? kCandMax : cap);
@@ -999,9 +1001,10 @@ static LocalWs carve_local(void* base, int64_t N, int H, int W, int64_t x_batch,
   w.pixrec = reinterpret_cast<int4*>(b + o);
   o += up256(npix_o * sizeof(int4));
   w.gpart = nullptr;
+  w.slices = slices;
   if (small) {
     w.gpart = reinterpret_cast<float*>(b + o);
-    o += up256((size_t)kSplitMax * 3 * npix_o * sizeof(float));
+    o += up256((size_t)slices * 3 * npix_o * sizeof(float));
   }
   w.maxbits = nullptr;
   w.touched = nullptr;
@@ -1026,8 +1029,8 @@ size_t local_det_workspace_bytes(int64_t N, int C, int H, int W, int64_t x_batch
 }
 
 // the caller does not tell the layout when it asks: size for the larger (global-list) scheme
-size_t gather_workspace_bytes(int64_t N, int H, int W, int64_t x_batch) {
-  const size_t a = carve(nullptr, N, H, W, x_batch).bytes, b = carve_local(nullptr, N, H, W, x_batch).bytes;
+size_t gather_workspace_bytes(int64_t N, int C, int H, int W, int64_t x_batch) {
+  const size_t a = carve(nullptr, N, H, W, x_batch).bytes, b = carve_local(nullptr, N, H, W, x_batch, C).bytes;
   return a > b ? a : b;
 }
 
@@ -1191,14 +1194,7 @@ int launch_bwd_gather(const BwdParams& pin, Layout lx, void* workspace, size_t w
     p.pixrec = w.pixrec;
     p.gpart = w.gpart;
     p.ovf_stride = (int64_t)w.ovf_stride;
-    if (w.gpart && !det) {
-      // small pyramid level: slice the channels over blockIdx.y until the grid fills the machine (slices of
-      // whole 256-byte rows); every pass of this call uses the same slicing
-      const int tiles = (int)(d.N * ((d.H + 7) / 8) * ((d.W + 31) / 32));
-      int C4 = d.C / 4;
-      while (tiles * (d.C / 4 / C4) < kSplitTiles && (d.C / 4 / C4) < kSplitMax && C4 % 2 == 0 && C4 / 2 >= 16) C4 /= 2;
-      p.cchunk = C4 * 4;
-    }
+    p.cchunk = d.C / w.slices;  // small pyramid level: every pass of this call uses the same channel slicing
     p.ovf = w.ovf;
     p.ovf_count = w.ovf_count;
     p.ovf_list = w.ovf_list;

@@ -324,9 +324,7 @@ static int launch_nhwc(FwdParams p, cudaStream_t st) {
   // small pyramid levels have fewer tiles than the machine has CTA slots: slice the channels over
   // blockIdx.y (each slice recomputes the tile geometry; slices stay whole 256-byte rows)
   const Dims& d = p.d;
-  const int tiles = d.N * ((d.H + 7) / 8) * ((d.W + 31) / 32);
-  int C4 = d.C / 4;
-  while (tiles * (d.C / 4 / C4) < sm_count() * 6 && C4 % 2 == 0 && C4 / 2 >= 16) C4 /= 2;
+  const int C4 = d.C / 4 / channel_slices(d.N, d.C, d.H, d.W);
   p.cchunk = C4 * 4;
   switch (C4) {
     case 1: return launch_nhwc_t<1, 1>(p, st);

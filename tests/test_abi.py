@@ -87,8 +87,9 @@ def test_workspace_size_contract():
     #  "tiles binned" counter behind the counters) and 8 in-line (src, w) entries; per output pixel a 1 B
     #  overflow flag and a 4 B overflow-list slot; each block rounded up to 256 B.
     #  channels-last local binning: tile counters, overflow flags, candidate segments (8 B each, 96 per tile and
-    #  source frame), overflow list, 16 B pixel records; levels with fewer than 592 tiles (4 per SM) also get room
-    #  for a channel-sliced gather: 1 + 8 flag arrays / list segments and 8 slices of grad-flow / grad-mask partials.
+    #  source frame), overflow list, 16 B pixel records; levels with fewer than 1184 tiles (8 per SM) and at least
+    #  128 channels are channel-sliced (2, 4 or 8 slices of >= 64 channels): 1 + slices flag arrays / list segments
+    #  and one grad-flow / grad-mask partial-sum buffer per slice.
     up = lambda v: (v + 255) // 256 * 256  # noqa: E731
 
     def global_lists(N, H, W, B):
@@ -99,16 +100,20 @@ def test_workspace_size_contract():
         tiles_per = ((H + 7) // 8) * ((W + 31) // 32)
         ntile, npo, npd = B * tiles_per, N * H * W, B * H * W
         cap = min(256, 96 * (N // B))
-        small = N * tiles_per < 592
-        nov = 9 if small else 1
+        slices, c4 = 1, C // 4
+        while (not det and C % 4 == 0 and N * tiles_per * slices < 1184 and slices < 8 and c4 % 2 == 0
+               and c4 // 2 >= 16):
+            slices, c4 = slices * 2, c4 // 2
+        nov = 1 + slices if slices > 1 else 1
         v = up(4 * (ntile + 1)) + nov * up(npo) + up(8 * ntile * cap) + up(4 * nov * npo) + up(16 * npo)
-        if small:
-            v += up(8 * 3 * npo * 4)
+        if slices > 1:
+            v += up(slices * 3 * npo * 4)
         if det:  # + scale bits, touched flags and the int64 overflow rows
             v += 256 + up(npd) + up(8 * npd * C)
         return v
 
-    for (N, C, H, W, B) in [(4, 8, 16, 32, 4), (40, 64, 256, 512, 40), (10, 8, 16, 32, 2)]:
+    for (N, C, H, W, B) in [(4, 8, 16, 32, 4), (40, 64, 256, 512, 40), (10, 8, 16, 32, 2), (2, 256, 8, 16, 2),
+                            (40, 512, 8, 16, 40), (40, 128, 64, 128, 40)]:
         assert _lib.bwd_workspace_bytes(N, C, H, W, B, True, 0) == 256 + max(global_lists(N, H, W, B),
                                                                             local(N, C, H, W, B))
     assert _lib.bwd_workspace_bytes(4, 8, 16, 32, 4, True, _lib.FLAG_BWD_ATOMIC) == 256
@@ -121,6 +126,8 @@ def test_workspace_size_contract():
         256 + max(2 * 8 * 16 * 32 * 8, local(10, 8, 16, 32, 2, True)))
     assert _lib.bwd_workspace_bytes(40, 64, 256, 512, 40, True, _lib.FLAG_DETERMINISTIC) == (
         256 + max(40 * 64 * 256 * 512 * 8, local(40, 64, 256, 512, 40, True)))
+    assert _lib.bwd_workspace_bytes(2, 256, 8, 16, 2, True, _lib.FLAG_DETERMINISTIC) == (
+        256 + max(2 * 256 * 8 * 16 * 8, local(2, 256, 8, 16, 2, True)))
     assert _lib.bwd_workspace_bytes(4, 8, 16, 32, 4, False, _lib.FLAG_DETERMINISTIC) == 256
 
 

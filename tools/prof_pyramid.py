@@ -20,6 +20,7 @@ ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--once", action="store_true")
 ap.add_argument("--layout", default="nhwc")
 ap.add_argument("--flags", default="0")
+ap.add_argument("--graph-only", action="store_true")
 ap.add_argument("--only-c", type=int, default=0, help="run only the levels with this channel count")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
@@ -70,7 +71,7 @@ for (c, h, w) in LEVELS:
         step(), step()
         torch.cuda.synchronize()
         continue
-    ev_us, wall_us = min(timed(step, a.iters) for _ in range(3))  # host-bound levels: best of three
+    ev_us, wall_us = (0.0, 0.0) if a.graph_only else min(timed(step, a.iters) for _ in range(3))  # best of three
     # graph replay: the same launches without the host
     s = torch.cuda.Stream()
     s.wait_stream(torch.cuda.current_stream())
@@ -82,7 +83,7 @@ for (c, h, w) in LEVELS:
     with torch.cuda.graph(g):
         step()
     gr_us, _ = timed(g.replay, a.iters)
-    th_us, _ = timed(lambda: torch_step(x, flow, mask, gout), max(3, a.iters // 4))
+    th_us = 0.0 if a.graph_only else timed(lambda: torch_step(x, flow, mask, gout), max(3, a.iters // 4))[0]
     by = fwd_bytes(N, c, h, w) + bwd_bytes(N, c, h, w)
     print(f"C={c:4d} {h:4d}x{w:<4d} N={N}: eager {ev_us:8.1f} us (host wall {wall_us:7.1f}), graph {gr_us:8.1f} us "
           f"= {by / gr_us / 1e3:7.1f} GB/s, torch composition {th_us:9.1f} us, bytes {by / 1e6:8.1f} MB", flush=True)
