@@ -41,7 +41,14 @@ def synth(N, C, H, W, oob, seed, device, pin=False):
     """Synthetic inputs of SURVEY.md section 8d: x ~ N(0,1); flow = 8 px low-frequency field +
     N(0,1) px noise (or the large / out-of-bounds variant); mask = sigmoid(N(0,1)); gout ~ N(0,1)."""
     g = torch.Generator().manual_seed(seed)
-    x = torch.randn(N, C, H, W, generator=g)
+    big = N * C * H * W >= 2 ** 31 and not pin and torch.device(device).type == "cuda"
+    if big:
+        # full-resolution shards (17 GB per tensor): generate the two large tensors on the device instead of
+        # holding them in host memory once per rank
+        gd = torch.Generator(device=device).manual_seed(seed)
+        x = torch.randn(N, C, H, W, generator=gd, device=device)
+    else:
+        x = torch.randn(N, C, H, W, generator=g)
     ii = torch.arange(H, dtype=torch.float32).view(1, H, 1)
     jj = torch.arange(W, dtype=torch.float32).view(1, 1, W)
     two_pi = 6.283185307179586
@@ -54,7 +61,7 @@ def synth(N, C, H, W, oob, seed, device, pin=False):
         sel = torch.rand(N, 1, H, W, generator=g) < 0.05
         flow = torch.where(sel, torch.sign(flow) * 10.0 * W, flow)
     mask = torch.sigmoid(torch.randn(N, 1, H, W, generator=g))
-    gout = torch.randn(N, C, H, W, generator=g)
+    gout = torch.randn(N, C, H, W, generator=gd, device=device) if big else torch.randn(N, C, H, W, generator=g)
     ts = [x, flow.contiguous(), mask, gout]
     if pin:
         return [t.pin_memory() for t in ts]
@@ -70,39 +77,61 @@ def bwd_bytes(N, C, H, W):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons of the GPUs in use, sampled while the timed region runs.  The sampler is
+    started before the region and waits for its first row (nvidia-smi takes over a second to come up on an 8-GPU
+    box); rows are time-stamped and `summary()` keeps the ones that fall between `begin()` and `end()`."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, indices):
+        self.indices = list(indices)
+        self.rows, self.proc, self.t0, self.t1 = [], None, None, None
 
     def __enter__(self):
+        if not self.indices:
+            return self
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", ",".join(str(i) for i in self.indices),
+                                          "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            deadline = time.perf_counter() + 15.0
+            while not self.rows and time.perf_counter() < deadline and self.proc.poll() is None:
+                time.sleep(0.01)
         except OSError:
             self.proc = None
         return self
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def begin(self):
+        self.t0 = time.perf_counter()
+
+    def end(self):
+        self.t1 = time.perf_counter()
 
     def __exit__(self, *a):
         if self.proc is not None:
-            time.sleep(0.15)
+            time.sleep(0.1)  # one more sampling period: a short region still gets the row that closes it
             self.proc.terminate()
             self.t.join(2)
 
     def summary(self):
-        sm, mx, reasons = [], 0.0, set()
+        if not self.indices:
+            return None
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        t0, t1 = self.t0 or 0.0, (self.t1 or float("inf")) + 0.05
+        inside = [r for (t, r) in self.rows if t0 <= t <= t1]
+        widened = False
+        if not inside:  # region shorter than one sampling period of a many-GPU query: nearest rows instead
+            inside = [r for (t, r) in self.rows if t0 - 0.3 <= t <= t1 + 0.3]
+            widened = True
+        sm, mx, reasons = [], 0.0, set()
+        for r in inside:
             try:
                 sm.append(float(r[0]))
                 mx = max(mx, float(r[1]))
@@ -115,7 +144,7 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         busy = [v for v in sm if v > 0.5 * max(sm)] or sm
         return {"sm_mhz": statistics.median(busy), "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "gpus": len(self.indices), **({"window": "+-0.3 s"} if widened else {})}
 
 
 def measured_peak():
@@ -223,13 +252,16 @@ def run_ours(args):
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = _lib.launch_count()
-    with ClockSampler(local_rank) as clk:
+    # rank 0 samples the clocks of every GPU of the job (the ranks use GPUs 0 .. world-1 of the box)
+    with ClockSampler(range(world) if rank == 0 else []) as clk:
         barrier()
+        clk.begin()
         t_begin.record()
         for k in range(args.steps):
             step(evs[k])
         t_end.record()
         barrier()
+        clk.end()
     launches = _lib.launch_count() - launches0
     ms_total = t_begin.elapsed_time(t_end)
     fwd_ms = statistics.mean(e[0].elapsed_time(e[1]) for e in evs)
