@@ -17,7 +17,9 @@ class HostWarpPlan:
     """Pre-allocated device staging + pinned host outputs for N frames of [C,H,W].
 
     run(hx, hflow, hmask, hgout) -> (out, gx, gflow, gmask) pinned host tensors, valid once the
-    current stream has been synchronised (the call itself is asynchronous).
+    current stream has been synchronised (the call itself is asynchronous).  The returned tensors are
+    the plan's own buffers: the next run() overwrites them, and consecutive calls overlap (the next
+    call's uploads start while this call's results are still going out).
     """
 
     def __init__(self, N, C, H, W, device, chunks=8, nhwc=False, padding="border", deterministic=False):
@@ -48,6 +50,11 @@ class HostWarpPlan:
         self.s_in = torch.cuda.Stream(device=d)
         self.s_cmp = torch.cuda.Stream(device=d)
         self.s_out = torch.cuda.Stream(device=d)
+        # per chunk: "compute has read the staged inputs" / "the results have left the device" of the previous
+        # run() -- consecutive calls pipeline into each other instead of draining the three streams in between
+        self.ev_cmp = [None] * self.chunks
+        self.ev_out = [None] * self.chunks
+        self.primed = False
         elems_in = N * H * W * (2 * C + 3)
         elems_out = N * H * W * (2 * C + 3)
         self.h2d_bytes = 4 * elems_in
@@ -56,14 +63,22 @@ class HostWarpPlan:
     def run(self, hx, hflow, hmask, hgout):
         N, C, H, W = self.N, self.C, self.H, self.W
         cur = torch.cuda.current_stream(self.device)
-        for s in (self.s_in, self.s_cmp, self.s_out):
-            s.wait_stream(cur)
+        if not self.primed:  # first call: whatever allocated / touched the staging buffers on `cur` comes first
+            for s in (self.s_in, self.s_cmp, self.s_out):
+                s.wait_stream(cur)
+            self.primed = True
         with torch.cuda.device(self.device):
             for k in range(self.chunks):
                 a, b = shard_range(N, k, self.chunks)
                 if a == b:
                     continue
                 sl = slice(a, b)
+                # staging buffers are reused by the next call: chunk k's inputs may be overwritten once the previous
+                # call's kernels have read them, its results once they have been copied out
+                if self.ev_cmp[k] is not None:
+                    self.s_in.wait_event(self.ev_cmp[k])
+                if self.ev_out[k] is not None:
+                    self.s_cmp.wait_event(self.ev_out[k])
                 with torch.cuda.stream(self.s_in):
                     self.x[sl].copy_(hx[sl], non_blocking=True)
                     self.flow[sl].copy_(hflow[sl], non_blocking=True)
@@ -82,13 +97,14 @@ class HostWarpPlan:
                                     self.gmask[sl].data_ptr(), None, b - a, C, H, W, b - a, xs,
                                     self.gout[sl].stride(), self.padding, self.flags, ws.data_ptr(), ws.numel(), st)
                 ev_c = self.s_cmp.record_event()
+                self.ev_cmp[k] = ev_c
                 self.s_out.wait_event(ev_c)
                 with torch.cuda.stream(self.s_out):
                     self.h_out[sl].copy_(self.out[sl], non_blocking=True)
                     self.h_gx[sl].copy_(self.gx[sl], non_blocking=True)
                     self.h_gflow[sl].copy_(self.gflow[sl], non_blocking=True)
                     self.h_gmask[sl].copy_(self.gmask[sl], non_blocking=True)
+                    self.ev_out[k] = self.s_out.record_event()
+        # the caller's stream sees the results of THIS call (the plan's own streams run ahead into the next one)
         cur.wait_stream(self.s_out)
-        cur.wait_stream(self.s_cmp)
-        cur.wait_stream(self.s_in)
         return self.h_out, self.h_gx, self.h_gflow, self.h_gmask

@@ -375,6 +375,41 @@ def test_non_default_stream_and_noncontiguous_inputs(dev):
     check(ours, run_ref(xs.contiguous(), flow, mask, gout))
 
 
+@pytest.mark.parametrize("nhwc", [False, True], ids=["nchw", "nhwc"])
+def test_host_buffer_plan_pipelines_consecutive_calls(dev, nhwc):
+    """HostWarpPlan (pinned host tensors in and out, three streams): consecutive calls overlap, so each call's
+    results must still be those of its own inputs."""
+    from c2m_b200.host import HostWarpPlan
+    N, C, H, W = 6, 8, 24, 40
+    plan = HostWarpPlan(N, C, H, W, dev, chunks=4, nhwc=nhwc)
+    fmt = torch.channels_last if nhwc else torch.contiguous_format
+    for seed in (1, 2, 3):
+        x, flow, mask, gout = [t.cpu() for t in make_inputs(dev, N, C, H, W, seed=seed)]
+        hx = x.contiguous(memory_format=fmt).pin_memory()
+        hg = gout.contiguous(memory_format=fmt).pin_memory()
+        res = plan.run(hx, flow.pin_memory(), mask.pin_memory(), hg)
+        torch.cuda.current_stream(dev).synchronize()
+        got = [t.clone() for t in res]
+        ref = run_ref(x.to(dev), flow.to(dev), mask.to(dev), gout.to(dev))
+        assert rel(got[0], ref[0]) <= FWD_TOL
+        for a, b in zip(got[1:], ref[1]):
+            assert rel(a, b) <= GRAD_TOL
+    # back-to-back calls without a synchronisation in between: the last call's results win
+    ins = []
+    for seed in (4, 5):
+        x, flow, mask, gout = [t.cpu() for t in make_inputs(dev, N, C, H, W, seed=seed)]
+        ins.append((x, flow, mask, gout, x.contiguous(memory_format=fmt).pin_memory(), flow.pin_memory(),
+                    mask.pin_memory(), gout.contiguous(memory_format=fmt).pin_memory()))
+    for it in ins:
+        res = plan.run(*it[4:])
+    torch.cuda.current_stream(dev).synchronize()
+    x, flow, mask, gout = ins[-1][:4]
+    ref = run_ref(x.to(dev), flow.to(dev), mask.to(dev), gout.to(dev))
+    assert rel(res[0], ref[0]) <= FWD_TOL
+    for a, b in zip(res[1:], ref[1]):
+        assert rel(a, b) <= GRAD_TOL
+
+
 def test_runs_in_float32_under_autocast(dev):
     x, flow, mask, gout = make_inputs(dev, 2, 8, 16, 32, seed=31)
     ref = run_ours(x, flow, mask, gout)
