@@ -39,6 +39,9 @@ SYMBOLS = (
     "c2m_occlusion_map_workspace_bytes",
     "c2m_warp_profile",
     "c2m_warp_profile_last_ms",
+    "c2m_warped_l1_workspace_bytes",
+    "c2m_warped_l1_fwd",
+    "c2m_warped_l1_bwd",
 )
 
 _lock = threading.Lock()
@@ -97,6 +100,13 @@ def load(build_if_missing: bool = False) -> ctypes.CDLL:
         lib.c2m_occlusion_map_workspace_bytes.argtypes = [_i64, _int, _int]
         lib.c2m_occlusion_map.restype = _int
         lib.c2m_occlusion_map.argtypes = [_ptr, _ptr, _i64, _int, _int, _int, _ptr, ctypes.c_size_t, _ptr]
+        lib.c2m_warped_l1_workspace_bytes.restype = ctypes.c_size_t
+        lib.c2m_warped_l1_workspace_bytes.argtypes = []
+        lib.c2m_warped_l1_fwd.restype = _int
+        lib.c2m_warped_l1_fwd.argtypes = [_ptr, _ptr, _ptr, _ptr, _i64, _int, _int, _int, _int, _ptr, ctypes.c_size_t,
+                                          _ptr]
+        lib.c2m_warped_l1_bwd.restype = _int
+        lib.c2m_warped_l1_bwd.argtypes = [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _int, _int, _int, _int, _ptr]
         _lib = lib
     return _lib
 
@@ -150,6 +160,20 @@ def occlusion_map(in_ptr, out_ptr, N, H, W, flags, ws_ptr, ws_bytes, stream) -> 
 
 def occlusion_map_workspace_bytes(N, H, W) -> int:
     return int(load().c2m_occlusion_map_workspace_bytes(N, H, W))
+
+
+def warped_l1_workspace_bytes() -> int:
+    return int(load().c2m_warped_l1_workspace_bytes())
+
+
+def warped_l1_fwd(src_ptr, flows_ptr, tgt_ptr, loss_ptr, B, C, T, H, W, ws_ptr, ws_bytes, stream) -> None:
+    _check(load().c2m_warped_l1_fwd(src_ptr, flows_ptr, tgt_ptr, loss_ptr, B, C, T, H, W, ws_ptr, ws_bytes, stream),
+           "c2m_warped_l1_fwd")
+
+
+def warped_l1_bwd(src_ptr, flows_ptr, tgt_ptr, gloss_ptr, gflows_ptr, gtargets_ptr, B, C, T, H, W, stream) -> None:
+    _check(load().c2m_warped_l1_bwd(src_ptr, flows_ptr, tgt_ptr, gloss_ptr, gflows_ptr, gtargets_ptr, B, C, T, H, W,
+                                    stream), "c2m_warped_l1_bwd")
 
 
 def profile(enable: bool) -> None:

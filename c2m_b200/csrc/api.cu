@@ -147,7 +147,7 @@ static void canonical(int64_t dst[4], const int64_t src[4], Layout l, int C, int
   }
 }
 
-static int fill_dims(Dims& d, int64_t N, int C, int H, int W, int64_t x_batch, int padding, int flags) {
+int fill_dims(Dims& d, int64_t N, int C, int H, int W, int64_t x_batch, int padding, int flags) {
   if (N < 0 || C < 0 || H < 0 || W < 0 || N > 0x7fffffff) {
     set_error("invalid sizes N=%lld C=%d H=%d W=%d", (long long)N, C, H, W);
     return C2M_ERR_INVALID;

@@ -329,6 +329,8 @@ void count_launch(int n = 1);
 int sm_count();
 // L2 prefetch distance of the channels-last kernels, in tiles (< 0: off); the environment variable
 // C2M_WARP_PREFETCH_TILES overrides the kernel's default (tuning hook)
+// sizes + the fp32 coordinate constants of the reference's grid arithmetic (validates; sets the error text)
+int fill_dims(Dims& d, int64_t N, int C, int H, int W, int64_t x_batch, int padding, int flags);
 int prefetch_tiles(int dflt);
 // number of blockIdx.y channel slices the channels-last kernels use for a level (1: none)
 int channel_slices(int64_t N, int C, int H, int W);

@@ -114,6 +114,20 @@ C2M_API size_t c2m_occlusion_map_workspace_bytes(int64_t N, int H, int W);
 C2M_API int c2m_occlusion_map(const float* in, float* out, int64_t N, int H, int W, int flags, void* workspace,
                               size_t workspace_bytes, void* cuda_stream);
 
+/* Fused warped-frame L1 loss (reference src/losses/losses.py:219-222: T calls of utils.resample on the source frame,
+ * torch.cat, then L1MaskedLoss without a mask, losses.py:184-189):
+ *   loss = mean over (b,c,t,i,j) of | resample(source, flows[:,:,t])[b,c,i,j] - targets[b,c,t,i,j] |
+ * source [B,C,H,W], flows [B,2,T,H,W] (pixels, channel 0 = x), targets [B,C,T,H,W], all contiguous float32 device
+ * memory; loss / gloss: one float in device memory.  The sum is formed from per-block partial sums in double, in a
+ * fixed order (bitwise reproducible).  Backward writes d loss / d flows (all of it) and, when asked, d loss / d targets;
+ * the source frame is data in the reference and gets no gradient here.  workspace: c2m_warped_l1_workspace_bytes(). */
+C2M_API size_t c2m_warped_l1_workspace_bytes(void);
+C2M_API int c2m_warped_l1_fwd(const float* source, const float* flows, const float* targets, float* loss, int64_t B,
+                              int C, int T, int H, int W, void* workspace, size_t workspace_bytes, void* cuda_stream);
+C2M_API int c2m_warped_l1_bwd(const float* source, const float* flows, const float* targets, const float* gloss,
+                              float* gflows /* nullable */, float* gtargets /* nullable */, int64_t B, int C, int T,
+                              int H, int W, void* cuda_stream);
+
 /* Measurement hook (process wide, off by default, not meant for concurrent callers).  While enabled, every
  * forward / backward call brackets its
  * dominant kernel -- the fused forward kernel; the gather kernel of the backward -- with a pair of CUDA events on the

@@ -98,3 +98,11 @@ def warp_blend(x, flow, mask=None, other=None):
     if other is None:
         return w * mask
     return w * mask + (1.0 - mask) * other
+
+
+def warped_l1(source: torch.Tensor, flows: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
+    """The `warped` term of the training losses (src/losses/losses.py:219-222): the source frame warped by each of
+    the T backward flows, stacked on a frame axis, L1 against the target frames (L1MaskedLoss without a mask,
+    losses.py:184-189, i.e. F.l1_loss with mean reduction)."""
+    frames = [resample(source, flows[:, :, t]).unsqueeze(2) for t in range(flows.shape[2])]
+    return F.l1_loss(torch.cat(frames, dim=2), targets)
