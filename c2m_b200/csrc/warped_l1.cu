@@ -29,13 +29,27 @@ struct L1Pixel {
 __device__ __forceinline__ L1Pixel l1_decode(const L1Params& p, int64_t idx) {
   const int HW = p.d.H * p.d.W;
   L1Pixel q;
-  const int64_t f = idx / HW;
-  q.r = (int)(idx - f * HW);
-  q.b = (int)(f / p.T);
-  q.t = (int)(f - (int64_t)q.b * p.T);
-  q.i = q.r / p.d.W;
+  if (p.total <= 0x7fffffff) {  // 32-bit divisions: the 64-bit ones are emulated and would dominate the kernel
+    const unsigned u = (unsigned)idx, f = u / (unsigned)HW;
+    q.r = (int)(u - f * (unsigned)HW);
+    q.b = (int)(f / (unsigned)p.T);
+    q.t = (int)(f - (unsigned)q.b * (unsigned)p.T);
+  } else {
+    const int64_t f = idx / HW;
+    q.r = (int)(idx - f * HW);
+    q.b = (int)(f / p.T);
+    q.t = (int)(f - (int64_t)q.b * p.T);
+  }
+  q.i = (int)((unsigned)q.r / (unsigned)p.d.W);
   q.j = q.r - q.i * p.d.W;
   return q;
+}
+
+__device__ __forceinline__ void l1_fetch(const L1Params& p, int64_t idx, int HW, L1Pixel& q, float& fx, float& fy) {
+  q = l1_decode(p, idx);
+  const float* fl = p.flows + ((int64_t)q.b * 2 * p.T + q.t) * HW + q.r;
+  fx = __ldg(fl);
+  fy = __ldg(fl + (int64_t)p.T * HW);
 }
 
 // bilinear sample of channel plane `xc`, in the accumulation order of the warp kernels (bit-equal to ATen's)
@@ -48,17 +62,23 @@ __device__ __forceinline__ float l1_sample(const float* xc, const Geo& g, int W,
   return fmaf(vse, g.wse, fmaf(vsw, g.wsw, fmaf(vne, g.wne, vnw * g.wnw)));
 }
 
-__global__ void __launch_bounds__(256) warped_l1_fwd_kernel(const L1Params p, double* __restrict__ partials) {
+__global__ void __launch_bounds__(256, 4) warped_l1_fwd_kernel(const L1Params p, double* __restrict__ partials) {
   __shared__ float s_warp[8];
   const Dims& d = p.d;
   const int HW = d.H * d.W;
   float acc = 0.f;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < p.total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    const L1Pixel q = l1_decode(p, idx);
-    const float* fl = p.flows + ((int64_t)q.b * 2 * p.T + q.t) * HW + q.r;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // the next pixel's flow is fetched while this one is processed: one exposed memory round trip per pixel
+  L1Pixel qn;
+  float nfx = 0.f, nfy = 0.f;
+  if (idx < p.total) l1_fetch(p, idx, HW, qn, nfx, nfy);
+  for (; idx < p.total; idx += stride) {
+    const L1Pixel q = qn;
+    const float fx = nfx, fy = nfy;
+    if (idx + stride < p.total) l1_fetch(p, idx + stride, HW, qn, nfx, nfy);
     Geo g;
-    make_geo<false>(d, __ldg(fl), __ldg(fl + (int64_t)p.T * HW), q.i, q.j, g);
+    make_geo<false>(d, fx, fy, q.i, q.j, g);
     const float* xc = p.src + (int64_t)q.b * d.C * HW;
     const float* tc = p.tgt + ((int64_t)q.b * d.C * p.T + q.t) * HW + q.r;
     for (int c = 0; c < d.C; ++c) {
@@ -98,18 +118,24 @@ __global__ void __launch_bounds__(256) warped_l1_finish_kernel(const double* __r
 
 // d loss / d flows (and, optionally, d loss / d targets): g = gloss / numel, s_c = sign(warped_c - target_c)
 //   gflow_x = g * sum_c s_c * d warped_c / d ix * d ix / d flow_x     (the coordinate algebra of make_geo<true>)
-__global__ void __launch_bounds__(256) warped_l1_bwd_kernel(const L1Params p, const float* __restrict__ gloss,
+__global__ void __launch_bounds__(256, 3) warped_l1_bwd_kernel(const L1Params p, const float* __restrict__ gloss,
                                                             double numel, float* __restrict__ gflows,
                                                             float* __restrict__ gtargets) {
   const Dims& d = p.d;
   const int HW = d.H * d.W;
   const float gs = (float)((double)__ldg(gloss) / numel);
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < p.total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    const L1Pixel q = l1_decode(p, idx);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  L1Pixel qn;
+  float nfx = 0.f, nfy = 0.f;
+  if (idx < p.total) l1_fetch(p, idx, HW, qn, nfx, nfy);
+  for (; idx < p.total; idx += stride) {
+    const L1Pixel q = qn;
+    const float fx = nfx, fy = nfy;
+    if (idx + stride < p.total) l1_fetch(p, idx + stride, HW, qn, nfx, nfy);
     const int64_t fo = ((int64_t)q.b * 2 * p.T + q.t) * HW + q.r;
     Geo g;
-    make_geo<true>(d, __ldg(p.flows + fo), __ldg(p.flows + fo + (int64_t)p.T * HW), q.i, q.j, g);
+    make_geo<true>(d, fx, fy, q.i, q.j, g);
     const float* xc = p.src + (int64_t)q.b * d.C * HW;
     int64_t to = ((int64_t)q.b * d.C * p.T + q.t) * HW + q.r;
     float gix = 0.f, giy = 0.f;

@@ -44,8 +44,10 @@ class HostWarpPlan:
         self.h_gx = torch.empty((N, C, H, W), memory_format=fmt, **pin)
         self.h_gflow = torch.empty((N, 2, H, W), **pin)
         self.h_gmask = torch.empty((N, 1, H, W), **pin)
-        per = (N + self.chunks - 1) // self.chunks
-        ws_bytes = _lib.bwd_workspace_bytes(per, C, H, W, per, True, self.flags)
+        # chunk sizes differ by at most one frame; the workspace is not monotonic in the frame count (small
+        # chunks of many-channel levels are channel-sliced and need partial-sum buffers), so size for each
+        sizes = {b - a for a, b in (shard_range(N, k, self.chunks) for k in range(self.chunks)) if b > a}
+        ws_bytes = max(_lib.bwd_workspace_bytes(n, C, H, W, n, True, self.flags) for n in sizes)
         self.ws = [torch.empty(ws_bytes, dtype=torch.uint8, device=d) for _ in range(2)]
         self.s_in = torch.cuda.Stream(device=d)
         self.s_cmp = torch.cuda.Stream(device=d)

@@ -16,7 +16,13 @@ B, C, T, H, W = 8, 3, 5, 256, 512
 torch.manual_seed(0)
 source = torch.randn(B, C, H, W, device=dev)
 targets = torch.randn(B, C, T, H, W, device=dev)
-flows = (4 * torch.randn(B, 2, T, H, W, device=dev)).requires_grad_(True)
+# flows as in the headline benchmark: 8 px low-frequency field + 1 px noise
+ii = torch.arange(H, device=dev, dtype=torch.float32).view(1, 1, H, 1)
+jj = torch.arange(W, device=dev, dtype=torch.float32).view(1, 1, 1, W)
+fx = 8.0 * torch.sin(6.2831853 * ii / (H / 2.0)) * torch.cos(6.2831853 * jj / (W / 2.0))
+fy = 8.0 * torch.cos(6.2831853 * ii / (H / 2.0)) * torch.sin(6.2831853 * jj / (W / 2.0))
+flows = (torch.stack([fx.expand(B, T, H, W), fy.expand(B, T, H, W)], 1) + torch.randn(B, 2, T, H, W, device=dev))
+flows = flows.requires_grad_(True)
 
 
 def ref_resample(image, flow):
