@@ -704,7 +704,7 @@ __global__ void __launch_bounds__(256, 4) gather_nhwc_kernel(const __grid_consta
         }
         if (DO_GF) {
           // the pixel's own gout row (an L1 / L2 hit: its neighbours just gathered it) is fetched last, which
-          // keeps the merged batch inside the register budget of three CTAs per SM
+          // keeps the merged batch inside the register budget of four CTAs per SM (64 registers)
           dot_issue_g<LP, NQ>(gol, dr);
           dot_finish<NQ>(dr, sa, sb, sc, se);
         }

@@ -14,6 +14,8 @@
  *                        CPU-built float32 linspace grid).
  *   c2m_occlusion_map    src/utils/ops.py:205-275 `get_corresponding_map` / `get_occlusion_map` (the forward
  *                        splat that produces the warp's mask, dense_motion.py:148,151).
+ *   c2m_warped_l1_fwd/bwd  src/losses/losses.py:219-222: the T `resample` calls on the source frame, their
+ *                        torch.cat and L1MaskedLoss (losses.py:184-189, no mask), and its autograd.
  *
  * The reference's own native-operator convention (its only hand-written warp,
  * src/modules/third_party/resample2d/src/resample2d_cuda.cc:6-33) is followed where it makes
@@ -88,8 +90,9 @@ C2M_API int c2m_warp_blend_fwd(const float* x, const float* flow, const float* m
 /* Any of gx / gflow / gmask / gother may be NULL (<=> ctx.needs_input_grad false).  gx is fully
  * written by the call (zero-filled first when the scatter uses atomics); it has x's strides.
  * gout and gother have g_strides.  workspace: c2m_warp_bwd_workspace_bytes() bytes for the SAME
- * flags, 256-byte aligned, contents undefined on entry and exit (the query is not told the layout and
- * sizes for the larger of the channels-last and NCHW schemes). */
+ * flags AND the same N, C, H, W, x_batch (the size is not monotonic in N: small many-channel levels get extra
+ * room for the channel-sliced kernels), 256-byte aligned, contents undefined on entry and exit (the query is not
+ * told the layout and sizes for the larger of the channels-last and NCHW schemes). */
 C2M_API int c2m_warp_blend_bwd(const float* x, const float* flow, const float* mask, const float* other,
                        const float* gout, float* gx, float* gflow, float* gmask, float* gother,
                        int64_t N, int C, int H, int W, int64_t x_batch,
