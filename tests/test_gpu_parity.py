@@ -375,6 +375,24 @@ def test_non_default_stream_and_noncontiguous_inputs(dev):
     check(ours, run_ref(xs.contiguous(), flow, mask, gout))
 
 
+@pytest.mark.parametrize("layout", ["nchw", "nhwc"])
+def test_accuracy_against_fp64_yardstick(dev, layout):
+    """the same composition evaluated in float64 on the device is the accuracy yardstick --
+    this library must be no further from it than torch's own float32 path is (both carry the reference's fp32
+    coordinate rounding, amplified by W/2)."""
+    N, C, H, W = 4, 64, 64, 128
+    x, flow, mask, gout = make_inputs(dev, N, C, H, W, seed=11)
+    if layout == "nhwc":
+        x = x.contiguous(memory_format=torch.channels_last)
+    ours = run_ours(x, flow, mask, gout)
+    ref32 = run_ref(x, flow, mask, gout)
+    ref64 = run_ref(x.double(), flow.double(), mask.double(), gout.double())
+    names = ["out", "gx", "gflow", "gmask"]
+    for name, a, b, c in zip(names, [ours[0]] + ours[1], [ref32[0]] + ref32[1], [ref64[0]] + ref64[1]):
+        e_ours, e_ref = rel(a, c), rel(b, c)
+        assert e_ours <= 1.5 * e_ref + 5e-6, f"{name}: ours {e_ours:.3e} vs torch fp32 {e_ref:.3e} (to float64)"
+
+
 @pytest.mark.parametrize("nhwc", [False, True], ids=["nchw", "nhwc"])
 def test_host_buffer_plan_pipelines_consecutive_calls(dev, nhwc):
     """HostWarpPlan (pinned host tensors in and out, three streams): consecutive calls overlap, so each call's

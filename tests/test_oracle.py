@@ -163,3 +163,49 @@ def test_integer_shift_away_from_borders():
     flow = np.stack([np.broadcast_to(fx, (1, H, W)), np.broadcast_to(fy, (1, H, W))], 1)
     out, _ = wn.warp_blend_forward(x, flow, dtype=np.float64)
     assert np.allclose(out[..., : W - 2], x[..., 2:], atol=1e-9)
+
+
+# ------------------------------------------------------------------------------------------------
+# hypothesis-driven properties of the oracle: random shapes, flows and seeds
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+_shape = st.tuples(st.integers(1, 3), st.integers(1, 5), st.integers(2, 12), st.integers(2, 20))
+
+
+@settings(max_examples=30, deadline=None)
+@given(shape=_shape, seed=st.integers(0, 2 ** 16), amp=st.sampled_from([0.3, 2.0, 9.0, 60.0]),
+       padding=st.sampled_from(["border", "zeros"]))
+def test_property_linearity_mask_scaling_and_adjointness(shape, seed, amp, padding):
+    """For any shape / flow: the forward is linear in x and in the mask, and grad-input is the adjoint of the
+    forward (<gout, F(x)> == <F^T(gout), x>), in fp64 where the identities hold to rounding."""
+    N, C, H, W = shape
+    rng = np.random.default_rng(seed)
+    x1, x2 = rng.standard_normal((2, N, C, H, W))
+    flow = (rng.standard_normal((N, 2, H, W)) * amp).astype(np.float32)
+    mask = rng.random((N, 1, H, W))
+    gout = rng.standard_normal((N, C, H, W))
+    f = lambda x, m: wn.warp_blend_forward(x, flow, m, padding=padding, dtype=np.float64)[0]  # noqa: E731
+    assert np.allclose(f(2 * x1 - 3 * x2, mask), 2 * f(x1, mask) - 3 * f(x2, mask), atol=1e-10)
+    assert np.allclose(f(x1, 0.25 * mask), 0.25 * f(x1, mask), atol=1e-12)
+    r = wn.warp_blend_backward(x1, flow, mask, gout, padding=padding, dtype=np.float64)
+    lhs, rhs = float((gout * f(x1, mask)).sum()), float((r["gx"] * x1).sum())
+    assert abs(lhs - rhs) <= 1e-9 * (np.abs(gout).sum() + 1.0)
+    # grad-mask is the plain warp weighted by gout (mul backward, generator.py:93)
+    assert np.allclose(r["gmask"], (gout * f(x1, np.ones_like(mask))).sum(1, keepdims=True), atol=1e-10)
+
+
+@settings(max_examples=20, deadline=None)
+@given(shape=_shape, seed=st.integers(0, 2 ** 16))
+def test_property_border_clamp_is_idempotent_for_far_flows(shape, seed):
+    """Border padding: once a sample is outside the image, pushing it further out changes nothing, and the flow
+    gradient there is zero (clip_coordinates_set_grad)."""
+    N, C, H, W = shape
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((N, C, H, W)).astype(np.float32)
+    sign = np.where(rng.random((N, 2, H, W)) < 0.5, -1.0, 1.0)
+    far = (sign * 4.0 * max(H, W)).astype(np.float32)
+    o1, _ = wn.warp_blend_forward(x, far)
+    o2, _ = wn.warp_blend_forward(x, (3 * far).astype(np.float32))
+    assert np.array_equal(o1, o2)
+    r = wn.warp_blend_backward(x, far, None, np.ones_like(x))
+    assert np.all(r["gflow"] == 0)
