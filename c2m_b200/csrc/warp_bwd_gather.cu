@@ -125,7 +125,23 @@ __global__ void __launch_bounds__(256) segbin_kernel(const BwdParams p) {
   int xmin = INT_MAX, xmax = INT_MIN, ymin = INT_MAX, ymax = INT_MIN;
   int ys[4] = {0, 0, 0, 0}, xs[4] = {0, 0, 0, 0};
   bool act[4] = {false, false, false, false};
+  unsigned inimg = 0;  // corners inside the image
   const int idx = n * HW + i * d.W + j;
+  // deterministic mode, called once on every way out: per destination an upper bound of the contributions its
+  // list will see (all in-image corners, whatever their weight), or bit 30 for a contribution that goes to
+  // overflow_kernel instead; zero_hot_rows_kernel clears the accumulator rows of the destinations that can
+  // receive terms outside their 12-entry list (a per-tile mark written with plain stores instead of the
+  // bit-30 atomics was tried: the reads of the small mark array hot-spot L2 and it is slower)
+  auto tally = [&](unsigned ovfbits) {
+    if (!p.cnt) return;
+    int* c0 = p.cnt + (n % d.x_batch) * HW;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (inimg & (1u << k)) {
+        if (ovfbits & (1u << k)) atomicOr(c0 + ys[k] * d.W + xs[k], 0x40000000);  // (counts stay below 2^30)
+        else atomicAdd(c0 + ys[k] * d.W + xs[k], 1);
+      }
+  };
   if (live) {
     const float* fl = p.flow + (int64_t)n * 2 * HW + i * d.W + j;
     const float fx = __ldg(fl), fy = __ldg(fl + HW);
@@ -143,6 +159,7 @@ __global__ void __launch_bounds__(256) segbin_kernel(const BwdParams p) {
     act[1] = g.okne && g.wne * m != 0.f;
     act[2] = g.oksw && g.wsw * m != 0.f;
     act[3] = g.okse && g.wse * m != 0.f;
+    inimg = (unsigned)g.oknw | ((unsigned)g.okne << 1) | ((unsigned)g.oksw << 2) | ((unsigned)g.okse << 3);
 #pragma unroll
     for (int k = 0; k < 4; ++k)
       if (act[k]) {
@@ -154,7 +171,10 @@ __global__ void __launch_bounds__(256) segbin_kernel(const BwdParams p) {
   xmax = __reduce_max_sync(0xffffffffu, xmax);
   ymin = __reduce_min_sync(0xffffffffu, ymin);
   ymax = __reduce_max_sync(0xffffffffu, ymax);
-  if (xmax < xmin) return;  // nothing lands anywhere (all weights zero / out of bounds)
+  if (xmax < xmin) {  // nothing lands anywhere (all weights zero / out of bounds)
+    tally(0u);
+    return;
+  }
   const int tx0 = xmin / TW, ty0 = ymin / TH;
   const int ncols = xmax / TW - tx0 + 1, nrows = ymax / TH - ty0 + 1;
   const int ncell = ncols * nrows;
@@ -172,7 +192,10 @@ __global__ void __launch_bounds__(256) segbin_kernel(const BwdParams p) {
     }
     fail = __ballot_sync(0xffffffffu, !ok);
   }
-  if (fail == 0u) return;
+  if (fail == 0u) {
+    tally(0u);
+    return;
+  }
   unsigned ovf = 0;
 #pragma unroll
   for (int k = 0; k < 4; ++k)
@@ -182,6 +205,7 @@ __global__ void __launch_bounds__(256) segbin_kernel(const BwdParams p) {
     }
   // each pixel belongs to exactly one segment and no gather CTA runs yet: a plain byte store is race free
   const unsigned has = __ballot_sync(0xffffffffu, ovf != 0u);
+  tally(ovf);
   if (has == 0u) return;
   int base = 0;
   if (lane == __ffs(has) - 1) base = atomicAdd(p.ovf_count, __popc(has));
@@ -190,6 +214,27 @@ __global__ void __launch_bounds__(256) segbin_kernel(const BwdParams p) {
     p.ovf[idx] = (unsigned char)ovf;
     p.ovf_list[base + __popc(has & ((1u << lane) - 1u))] = idx;
   }
+}
+
+// Deterministic mode: clear the 64-bit accumulator rows of the destinations that can receive terms -- more
+// in-image corners than list slots, or a contribution handed to overflow_kernel -- instead of the whole
+// accumulator (one int64 per grad-input element).  One warp per 32 destinations.
+__global__ void __launch_bounds__(256) zero_hot_rows_kernel(const int* __restrict__ cnt, long long* __restrict__ acc,
+                                                            int64_t ndest, int C) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w0 = ((int64_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * 32;
+  if (w0 >= ndest) return;
+  const int64_t D = w0 + lane;
+  const bool hot = D < ndest && cnt[D] > kLocalCap;
+  const unsigned m = __ballot_sync(0xffffffffu, hot);
+  if (m == 0u) return;
+  // the warp's 32 rows are one contiguous block of 32 * C int64: 16-byte stores, lanes side by side, rows
+  // that are not hot skipped (C % 4 == 0 on this path)
+  int4* blk = reinterpret_cast<int4*>(acc + w0 * C);
+  const int per_row = C >> 1;  // int4 per row
+  const int nrows = (int)min((int64_t)32, ndest - w0);
+  for (int k = lane; k < nrows * per_row; k += 32)
+    if ((m >> (k / per_row)) & 1u) blk[k] = make_int4(0, 0, 0, 0);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -972,7 +1017,8 @@ struct LocalWs {
   unsigned* maxbits;
   unsigned char* touched;
   long long* acc64;
-  size_t det_clear_bytes;  // [maxbits | touched | acc64]
+  int* dcnt;               // in-image corners per destination (bit 30: a contribution was handed to overflow_kernel)
+  size_t det_clear_bytes;  // [maxbits | touched | dcnt]
 };
 
 static LocalWs carve_local(void* base, int64_t N, int H, int W, int64_t x_batch, int C, bool det = false) {
@@ -1009,6 +1055,7 @@ static LocalWs carve_local(void* base, int64_t N, int H, int W, int64_t x_batch,
   w.maxbits = nullptr;
   w.touched = nullptr;
   w.acc64 = nullptr;
+  w.dcnt = nullptr;
   w.det_clear_bytes = 0;
   if (det) {
     const size_t npix_d = (size_t)x_batch * H * W, o0 = o;
@@ -1016,9 +1063,12 @@ static LocalWs carve_local(void* base, int64_t N, int H, int W, int64_t x_batch,
     o += 256;
     w.touched = reinterpret_cast<unsigned char*>(b + o);
     o += up256(npix_d);
+    w.dcnt = reinterpret_cast<int*>(b + o);
+    o += up256(npix_d * sizeof(int));
+    w.det_clear_bytes = o - o0;
+    // not cleared as a whole: zero_hot_rows_kernel clears the rows that can receive terms
     w.acc64 = reinterpret_cast<long long*>(b + o);
     o += up256(npix_d * (size_t)C * sizeof(long long));
-    w.det_clear_bytes = o - o0;
   }
   w.bytes = o;
   return w;
@@ -1204,6 +1254,7 @@ int launch_bwd_gather(const BwdParams& pin, Layout lx, void* workspace, size_t w
       p.maxbits = w.maxbits;
       p.touched = w.touched;
       p.acc64 = w.acc64;
+      p.cnt = w.dcnt;
       int cl = 2;  // 4 corners
       const int64_t cnt = (int64_t)d.H * d.W * (d.N / d.x_batch);
       while ((1ll << (cl - 2)) < cnt) ++cl;
@@ -1219,8 +1270,10 @@ int launch_bwd_gather(const BwdParams& pin, Layout lx, void* workspace, size_t w
     segbin_kernel<<<dim3((unsigned)((segs + 7) / 8), (unsigned)d.N), 256, 0, st>>>(p);
     count_launch();
     if (det) {  // incoherent segments / failed registrations first: the gather folds their rows in
+      const int64_t ndest = (int64_t)d.x_batch * d.H * d.W;
+      zero_hot_rows_kernel<<<(unsigned)((ndest + 255) / 256), 256, 0, st>>>(w.dcnt, w.acc64, ndest, d.C);
       overflow_kernel<true, true><<<sm_count() * 8, 256, 0, st>>>(p);
-      count_launch();
+      count_launch(2);
     }
   } else if (p.gx) {
     const GatherWs w = carve(workspace, d.N, d.H, d.W, d.x_batch);

@@ -11,6 +11,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import c2m_b200  # noqa: E402
 
 dev = torch.device("cuda", 0)
+FORCE_DET = os.environ.get("C2M_STRESS_DET", "0") not in ("", "0")
 
 
 def ref(x, flow, mask, B):
@@ -56,7 +57,7 @@ def main(iters, seed):
             x = x.contiguous(memory_format=torch.channels_last)
         mask = torch.rand(N, 1, H, W, device=dev) if rnd.random() < 0.8 else None
         gout = torch.randn(N, C, H, W, device=dev)
-        det = rnd.random() < 0.25
+        det = FORCE_DET or rnd.random() < 0.25
         xs = [x.clone().requires_grad_(True) for _ in range(2)]
         fs = [flow.clone().requires_grad_(True) for _ in range(2)]
         ms = [None if mask is None else mask.clone().requires_grad_(True) for _ in range(2)]
@@ -64,7 +65,12 @@ def main(iters, seed):
         o2 = ref(xs[1], fs[1], ms[1], B)
         ins1 = [t for t in (xs[0], fs[0], ms[0]) if t is not None]
         ins2 = [t for t in (xs[1], fs[1], ms[1]) if t is not None]
-        g1 = torch.autograd.grad(o1, ins1, gout)
+        g1 = torch.autograd.grad(o1, ins1, gout, retain_graph=det)
+        if det:  # deterministic mode: a second backward of the same graph gives the same bits
+            g1b = torch.autograd.grad(o1, ins1, gout)
+            if not torch.equal(g1[0], g1b[0]):
+                print("NOT REPRODUCIBLE", it, dict(N=N, B=B, C=C, H=H, W=W, kind=kind, cl=not x.is_contiguous()))
+                return 1
         g2 = torch.autograd.grad(o2, ins2, gout)
         errs = {"out": rel(o1, o2), "gx": rel(g1[0], g2[0]), "gflow": rel(g1[1], g2[1])}
         if mask is not None:
