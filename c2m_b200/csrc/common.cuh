@@ -59,6 +59,8 @@ struct BwdParams {
   const unsigned* maxbits;  // bit pattern of max|gout*mask| (channels-last gather: [0] max|gout|, [1] max|mask|)
   int count_log2;           // ceil(log2(max contributions per destination))
   unsigned char* touched;   // deterministic channels-last gather: [x_batch*H*W] destination has terms in acc64
+  int* incoh;               // deterministic channels-last gather: [x_batch] incoherent segments seen per image
+  int incoh_thresh;         // more than this many: every accumulator row of the image is cleared
   // gather-form backward (contributor lists built by bin_kernel)
   int* cnt;                 // [x_batch*H*W] contributions seen per destination pixel
   void* entries;            // [x_batch*H*W][kListCap] ListEntry

@@ -132,14 +132,18 @@ __global__ void __launch_bounds__(256) segbin_kernel(const BwdParams p) {
   // overflow_kernel instead; zero_hot_rows_kernel clears the accumulator rows of the destinations that can
   // receive terms outside their 12-entry list (a per-tile mark written with plain stores instead of the
   // bit-30 atomics was tried: the reads of the small mark array hot-spot L2 and it is slower)
+  bool all_hot = false;  // this image already has so many incoherent segments that all its rows get cleared
   auto tally = [&](unsigned ovfbits) {
     if (!p.cnt) return;
     int* c0 = p.cnt + (n % d.x_batch) * HW;
 #pragma unroll
     for (int k = 0; k < 4; ++k)
       if (inimg & (1u << k)) {
-        if (ovfbits & (1u << k)) atomicOr(c0 + ys[k] * d.W + xs[k], 0x40000000);  // (counts stay below 2^30)
-        else atomicAdd(c0 + ys[k] * d.W + xs[k], 1);
+        if (ovfbits & (1u << k)) {
+          if (!all_hot) atomicOr(c0 + ys[k] * d.W + xs[k], 0x40000000);  // (counts stay below 2^30)
+        } else {
+          atomicAdd(c0 + ys[k] * d.W + xs[k], 1);
+        }
       }
   };
   if (live) {
@@ -181,6 +185,14 @@ __global__ void __launch_bounds__(256) segbin_kernel(const BwdParams p) {
   unsigned fail;
   if (ncell > kMaxCells) {
     fail = 0xffffffffu;
+    if (p.cnt) {
+      // deterministic mode: incoherent segments are counted per image; once an image has more than
+      // p.incoh_thresh of them zero_hot_rows_kernel clears all its rows, and later segments need not flag
+      // their destinations one by one (with fully incoherent flows that is four atomics per pixel saved)
+      int k = 0;
+      if (lane == 0) k = atomicAdd(p.incoh + n % d.x_batch, 1);
+      all_hot = __shfl_sync(0xffffffffu, k, 0) >= p.incoh_thresh;
+    }
   } else {
     bool ok = true;
     if (lane < ncell) {
@@ -219,13 +231,14 @@ __global__ void __launch_bounds__(256) segbin_kernel(const BwdParams p) {
 // Deterministic mode: clear the 64-bit accumulator rows of the destinations that can receive terms -- more
 // in-image corners than list slots, or a contribution handed to overflow_kernel -- instead of the whole
 // accumulator (one int64 per grad-input element).  One warp per 32 destinations.
-__global__ void __launch_bounds__(256) zero_hot_rows_kernel(const int* __restrict__ cnt, long long* __restrict__ acc,
-                                                            int64_t ndest, int C) {
+__global__ void __launch_bounds__(256) zero_hot_rows_kernel(const int* __restrict__ cnt, const int* __restrict__ incoh,
+                                                            int incoh_thresh, long long* __restrict__ acc,
+                                                            int64_t ndest, int HW, int C) {
   const int lane = threadIdx.x & 31;
   const int64_t w0 = ((int64_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * 32;
   if (w0 >= ndest) return;
   const int64_t D = w0 + lane;
-  const bool hot = D < ndest && cnt[D] > kLocalCap;
+  const bool hot = D < ndest && (cnt[D] > kLocalCap || incoh[D / HW] > incoh_thresh);
   const unsigned m = __ballot_sync(0xffffffffu, hot);
   if (m == 0u) return;
   // the warp's 32 rows are one contiguous block of 32 * C int64: 16-byte stores, lanes side by side, rows
@@ -1018,7 +1031,8 @@ struct LocalWs {
   unsigned char* touched;
   long long* acc64;
   int* dcnt;               // in-image corners per destination (bit 30: a contribution was handed to overflow_kernel)
-  size_t det_clear_bytes;  // [maxbits | touched | dcnt]
+  int* incoh;              // incoherent segments per image
+  size_t det_clear_bytes;  // [maxbits | touched | dcnt | incoh]
 };
 
 static LocalWs carve_local(void* base, int64_t N, int H, int W, int64_t x_batch, int C, bool det = false) {
@@ -1056,6 +1070,7 @@ static LocalWs carve_local(void* base, int64_t N, int H, int W, int64_t x_batch,
   w.touched = nullptr;
   w.acc64 = nullptr;
   w.dcnt = nullptr;
+  w.incoh = nullptr;
   w.det_clear_bytes = 0;
   if (det) {
     const size_t npix_d = (size_t)x_batch * H * W, o0 = o;
@@ -1065,6 +1080,8 @@ static LocalWs carve_local(void* base, int64_t N, int H, int W, int64_t x_batch,
     o += up256(npix_d);
     w.dcnt = reinterpret_cast<int*>(b + o);
     o += up256(npix_d * sizeof(int));
+    w.incoh = reinterpret_cast<int*>(b + o);
+    o += up256((size_t)x_batch * sizeof(int));
     w.det_clear_bytes = o - o0;
     // not cleared as a whole: zero_hot_rows_kernel clears the rows that can receive terms
     w.acc64 = reinterpret_cast<long long*>(b + o);
@@ -1255,6 +1272,9 @@ int launch_bwd_gather(const BwdParams& pin, Layout lx, void* workspace, size_t w
       p.touched = w.touched;
       p.acc64 = w.acc64;
       p.cnt = w.dcnt;
+      p.incoh = w.incoh;
+      // an image whose incoherent segments exceed 1/16 of all its segments gets every accumulator row cleared
+      p.incoh_thresh = (int)(((int64_t)d.H * ((d.W + 31) / 32) * (d.N / d.x_batch)) / 16);
       int cl = 2;  // 4 corners
       const int64_t cnt = (int64_t)d.H * d.W * (d.N / d.x_batch);
       while ((1ll << (cl - 2)) < cnt) ++cl;
@@ -1271,7 +1291,8 @@ int launch_bwd_gather(const BwdParams& pin, Layout lx, void* workspace, size_t w
     count_launch();
     if (det) {  // incoherent segments / failed registrations first: the gather folds their rows in
       const int64_t ndest = (int64_t)d.x_batch * d.H * d.W;
-      zero_hot_rows_kernel<<<(unsigned)((ndest + 255) / 256), 256, 0, st>>>(w.dcnt, w.acc64, ndest, d.C);
+      zero_hot_rows_kernel<<<(unsigned)((ndest + 255) / 256), 256, 0, st>>>(w.dcnt, w.incoh, p.incoh_thresh, w.acc64,
+                                                                              ndest, d.H * d.W, d.C);
       overflow_kernel<true, true><<<sm_count() * 8, 256, 0, st>>>(p);
       count_launch(2);
     }

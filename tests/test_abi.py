@@ -108,8 +108,8 @@ def test_workspace_size_contract():
         v = up(4 * (ntile + 1)) + nov * up(npo) + up(8 * ntile * cap) + up(4 * nov * npo) + up(16 * npo)
         if slices > 1:
             v += up(slices * 3 * npo * 4)
-        if det:  # + scale bits, touched flags, per-destination corner counts and the int64 overflow rows
-            v += 256 + up(npd) + up(4 * npd) + up(8 * npd * C)
+        if det:  # + scale bits, touched flags, per-destination corner counts, per-image incoherent-segment counters and the int64 overflow rows
+            v += 256 + up(npd) + up(4 * npd) + up(4 * B) + up(8 * npd * C)
         return v
 
     for (N, C, H, W, B) in [(4, 8, 16, 32, 4), (40, 64, 256, 512, 40), (10, 8, 16, 32, 2), (2, 256, 8, 16, 2),
