@@ -218,6 +218,12 @@ int c2m_warp_profile(int enable) {
   }
   g_prof.on = enable != 0;
   g_prof.valid = false;
+  if (!enable && g_prof.a) {
+    // the library keeps no CUDA objects alive while the hook is off (nothing to outlive the caller's context)
+    (void)cudaEventDestroy(g_prof.a);
+    (void)cudaEventDestroy(g_prof.b);
+    g_prof.a = g_prof.b = nullptr;
+  }
   return C2M_OK;
 }
 
