@@ -33,6 +33,9 @@ SYMBOLS = (
     "c2m_warp_blend_fwd",
     "c2m_warp_blend_bwd",
     "c2m_warp_bwd_workspace_bytes",
+    "c2m_warp_blend_fwd_rs",
+    "c2m_warp_blend_bwd_rs",
+    "c2m_warp_bwd_workspace_bytes_rs",
     "c2m_base_grid",
     "c2m_warp_launch_count",
     "c2m_occlusion_map",
@@ -51,6 +54,14 @@ _i64 = ctypes.c_int64
 _int = ctypes.c_int
 _ptr = ctypes.c_void_p
 _Strides = _i64 * 4
+
+RESIZE_HALF_PIXEL = 0        # generator.py:84-85,91-92: align_corners=False, flow values not rescaled
+RESIZE_CORNERS_RESCALE = 1   # utils.py:346-354: align_corners=True, flow values multiplied by new/old
+
+
+class Resize(ctypes.Structure):
+    """struct c2m_resize of include/c2m_warp.h: the sizes the flow / mask are passed at (0 = the feature size)."""
+    _fields_ = [("flow_h", _int), ("flow_w", _int), ("mask_h", _int), ("mask_w", _int), ("flow_mode", _int)]
 
 
 class C2MWarpError(RuntimeError):
@@ -90,6 +101,17 @@ def load(build_if_missing: bool = False) -> ctypes.CDLL:
                                            _ptr, ctypes.c_size_t, _ptr]
         lib.c2m_warp_bwd_workspace_bytes.restype = ctypes.c_size_t
         lib.c2m_warp_bwd_workspace_bytes.argtypes = [_i64, _int, _int, _int, _i64, _int, _int]
+        lib.c2m_warp_blend_fwd_rs.restype = _int
+        lib.c2m_warp_blend_fwd_rs.argtypes = [_ptr, _ptr, _ptr, _ptr, _ptr, _i64, _int, _int, _int, _i64,
+                                              ctypes.POINTER(_i64), ctypes.POINTER(_i64), ctypes.POINTER(Resize),
+                                              _int, _int, _ptr]
+        lib.c2m_warp_blend_bwd_rs.restype = _int
+        lib.c2m_warp_blend_bwd_rs.argtypes = [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr,
+                                              _i64, _int, _int, _int, _i64,
+                                              ctypes.POINTER(_i64), ctypes.POINTER(_i64), ctypes.POINTER(Resize),
+                                              _int, _int, _ptr, ctypes.c_size_t, _ptr]
+        lib.c2m_warp_bwd_workspace_bytes_rs.restype = ctypes.c_size_t
+        lib.c2m_warp_bwd_workspace_bytes_rs.argtypes = [_i64, _int, _int, _int, _i64, _int, ctypes.POINTER(Resize), _int]
         lib.c2m_base_grid.restype = _int
         lib.c2m_base_grid.argtypes = [_ptr, _i64, _int, _int, _ptr]
         lib.c2m_warp_profile.restype = _int
@@ -127,23 +149,38 @@ def strides4(s) -> "_Strides":
     return _strides_cached(tuple(int(v) for v in s))
 
 
+@functools.lru_cache(maxsize=256)
+def resize_spec(flow_h, flow_w, mask_h, mask_w, flow_mode):
+    """ctypes c2m_resize (cached) or None when nothing is resized."""
+    return Resize(int(flow_h), int(flow_w), int(mask_h), int(mask_w), int(flow_mode))
+
+
 def warp_blend_fwd(x_ptr, flow_ptr, mask_ptr, other_ptr, out_ptr, N, C, H, W, x_batch, x_strides, out_strides,
-                   padding, flags, stream) -> None:
-    rc = load().c2m_warp_blend_fwd(x_ptr, flow_ptr, mask_ptr, other_ptr, out_ptr, N, C, H, W, x_batch,
-                                   strides4(x_strides), strides4(out_strides), padding, flags, stream)
+                   padding, flags, stream, resize=None) -> None:
+    rc = load().c2m_warp_blend_fwd_rs(x_ptr, flow_ptr, mask_ptr, other_ptr, out_ptr, N, C, H, W, x_batch,
+                                      strides4(x_strides), strides4(out_strides), resize, padding, flags, stream)
     _check(rc, "c2m_warp_blend_fwd")
 
 
 def warp_blend_bwd(x_ptr, flow_ptr, mask_ptr, other_ptr, gout_ptr, gx_ptr, gflow_ptr, gmask_ptr, gother_ptr,
-                   N, C, H, W, x_batch, x_strides, g_strides, padding, flags, ws_ptr, ws_bytes, stream) -> None:
-    rc = load().c2m_warp_blend_bwd(x_ptr, flow_ptr, mask_ptr, other_ptr, gout_ptr, gx_ptr, gflow_ptr, gmask_ptr,
-                                   gother_ptr, N, C, H, W, x_batch, strides4(x_strides), strides4(g_strides),
-                                   padding, flags, ws_ptr, ws_bytes, stream)
+                   N, C, H, W, x_batch, x_strides, g_strides, padding, flags, ws_ptr, ws_bytes, stream,
+                   resize=None) -> None:
+    rc = load().c2m_warp_blend_bwd_rs(x_ptr, flow_ptr, mask_ptr, other_ptr, gout_ptr, gx_ptr, gflow_ptr, gmask_ptr,
+                                      gother_ptr, N, C, H, W, x_batch, strides4(x_strides), strides4(g_strides),
+                                      resize, padding, flags, ws_ptr, ws_bytes, stream)
     _check(rc, "c2m_warp_blend_bwd")
 
 
-def bwd_workspace_bytes(N, C, H, W, x_batch, want_gx, flags) -> int:
-    return int(load().c2m_warp_bwd_workspace_bytes(N, C, H, W, x_batch, int(bool(want_gx)), flags))
+@functools.lru_cache(maxsize=1024)
+def _ws_bytes_cached(N, C, H, W, x_batch, want_gx, flags, rs_key):
+    rs = None if rs_key is None else resize_spec(*rs_key)
+    return int(load().c2m_warp_bwd_workspace_bytes_rs(N, C, H, W, x_batch, want_gx, rs, flags))
+
+
+def bwd_workspace_bytes(N, C, H, W, x_batch, want_gx, flags, resize=None) -> int:
+    """Workspace size of the backward (cached per argument tuple: the query is a pure function of its arguments)."""
+    key = None if resize is None else (resize.flow_h, resize.flow_w, resize.mask_h, resize.mask_w, resize.flow_mode)
+    return _ws_bytes_cached(int(N), int(C), int(H), int(W), int(x_batch), int(bool(want_gx)), int(flags), key)
 
 
 def base_grid(grid_ptr, N, H, W, stream) -> None:

@@ -238,14 +238,18 @@ float c2m_warp_profile_last_ms(void) {
   return ms;
 }
 
-int c2m_warp_blend_fwd(const float* x, const float* flow, const float* mask, const float* other, float* out,
-                       int64_t N, int C, int H, int W, int64_t x_batch, const int64_t x_strides[4],
-                       const int64_t out_strides[4], int padding, int flags, void* cuda_stream) {
+static size_t up256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+int c2m_warp_blend_fwd_rs(const float* x, const float* flow, const float* mask, const float* other, float* out,
+                          int64_t N, int C, int H, int W, int64_t x_batch, const int64_t x_strides[4],
+                          const int64_t out_strides[4], const c2m_resize* rs, int padding, int flags,
+                          void* cuda_stream) {
   FwdParams p;
   memset(&p, 0, sizeof(p));
   int rc = fill_dims(p.d, N, C, H, W, x_batch, padding, flags);
   if (rc) return rc;
   if (N == 0 || C == 0 || H == 0 || W == 0) return C2M_OK;  // empty: nothing to write
+  if ((rc = fill_resize(p.d, rs)) != C2M_OK) return rc;
   if (!x || !flow || !out || !x_strides || !out_strides) {
     set_error("null pointer argument");
     return C2M_ERR_INVALID;
@@ -264,23 +268,56 @@ int c2m_warp_blend_fwd(const float* x, const float* flow, const float* mask, con
   return check_launch("c2m_warp_blend_fwd");
 }
 
+int c2m_warp_blend_fwd(const float* x, const float* flow, const float* mask, const float* other, float* out,
+                       int64_t N, int C, int H, int W, int64_t x_batch, const int64_t x_strides[4],
+                       const int64_t out_strides[4], int padding, int flags, void* cuda_stream) {
+  return c2m_warp_blend_fwd_rs(x, flow, mask, other, out, N, C, H, W, x_batch, x_strides, out_strides, nullptr, padding,
+                               flags, cuda_stream);
+}
+
+// fused-resize backward: [resized flow | resized mask | grad-flow at the feature size | grad-mask at the feature
+// size] in front of the workspace of the plain call
+static size_t resize_ws_bytes(int64_t N, int H, int W) {
+  const size_t px = (size_t)N * H * W * sizeof(float);
+  return 2 * up256(2 * px) + 2 * up256(px);
+}
+
+size_t c2m_warp_bwd_workspace_bytes_rs(int64_t N, int C, int H, int W, int64_t x_batch, int want_gx,
+                                       const c2m_resize* rs, int flags) {
+  size_t b = bwd_workspace_bytes(N, C, H, W, x_batch, want_gx, flags);
+  if (rs && N > 0 && H > 0 && W > 0) {
+    const bool on = (rs->flow_h > 0 && rs->flow_h != H) || (rs->flow_w > 0 && rs->flow_w != W) ||
+                    (rs->mask_h > 0 && rs->mask_h != H) || (rs->mask_w > 0 && rs->mask_w != W);
+    if (on) b += resize_ws_bytes(N, H, W);
+  }
+  return b;
+}
+
 size_t c2m_warp_bwd_workspace_bytes(int64_t N, int C, int H, int W, int64_t x_batch, int want_gx, int flags) {
   return bwd_workspace_bytes(N, C, H, W, x_batch, want_gx, flags);
 }
 
-int c2m_warp_blend_bwd(const float* x, const float* flow, const float* mask, const float* other, const float* gout,
-                       float* gx, float* gflow, float* gmask, float* gother, int64_t N, int C, int H, int W,
-                       int64_t x_batch, const int64_t x_strides[4], const int64_t g_strides[4], int padding,
-                       int flags, void* workspace, size_t workspace_bytes, void* cuda_stream) {
+int c2m_warp_blend_bwd_rs(const float* x, const float* flow, const float* mask, const float* other, const float* gout,
+                          float* gx, float* gflow, float* gmask, float* gother, int64_t N, int C, int H, int W,
+                          int64_t x_batch, const int64_t x_strides[4], const int64_t g_strides[4],
+                          const c2m_resize* rs, int padding, int flags, void* workspace, size_t workspace_bytes,
+                          void* cuda_stream) {
   BwdParams p;
   memset(&p, 0, sizeof(p));
   int rc = fill_dims(p.d, N, C, H, W, x_batch, padding, flags);
   if (rc) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
   if (N == 0 || H == 0 || W == 0) return C2M_OK;
+  if ((rc = fill_resize(p.d, rs)) != C2M_OK) return rc;
+  const Resize rsz = p.d.rs;
+  const size_t gflow_elems = (size_t)N * 2 * ((rsz.on & 1) ? (size_t)rsz.fh * rsz.fw : (size_t)H * W);
+  const size_t gmask_elems = (size_t)N * ((rsz.on & 2) ? (size_t)rsz.mh * rsz.mw : (size_t)H * W);
   if (C == 0) {  // no channels: flow / mask gradients are zero
-    if (gflow && cudaMemsetAsync(gflow, 0, (size_t)N * 2 * H * W * sizeof(float), st) != cudaSuccess) return C2M_ERR_CUDA;
-    if (gmask && cudaMemsetAsync(gmask, 0, (size_t)N * H * W * sizeof(float), st) != cudaSuccess) return C2M_ERR_CUDA;
+    if ((gflow && cudaMemsetAsync(gflow, 0, gflow_elems * sizeof(float), st) != cudaSuccess) ||
+        (gmask && cudaMemsetAsync(gmask, 0, gmask_elems * sizeof(float), st) != cudaSuccess)) {
+      set_error("c2m_warp_blend_bwd: cudaMemsetAsync: %s", cudaGetErrorString(cudaGetLastError()));
+      return C2M_ERR_CUDA;
+    }
     return C2M_OK;
   }
   if (!x || !flow || !gout || !x_strides || !g_strides) {
@@ -305,9 +342,43 @@ int c2m_warp_blend_bwd(const float* x, const float* flow, const float* mask, con
   p.x = x; p.flow = flow; p.mask = mask; p.other = other; p.gout = gout;
   p.gx = gx; p.gflow = gflow; p.gmask = gmask; p.gother = gother;
   p.cchunk = C;
+  if (rsz.on) {
+    // the resized flow / mask are materialised once (the forward computes them on the fly), the kernels below run on
+    // them unchanged, and the gradients go back through the resize in one gather pass
+    const size_t front = resize_ws_bytes(N, H, W);
+    if (!workspace || workspace_bytes < front + 256) {
+      set_error("workspace too small: %zu < %zu", workspace_bytes, front + 256);
+      return C2M_ERR_WORKSPACE;
+    }
+    const size_t px = (size_t)N * H * W * sizeof(float);
+    char* b = reinterpret_cast<char*>(workspace);
+    float* flow_s = reinterpret_cast<float*>(b);
+    float* mask_s = reinterpret_cast<float*>(b + up256(2 * px));
+    float* gflow_s = reinterpret_cast<float*>(b + up256(2 * px) + up256(px));
+    float* gmask_s = reinterpret_cast<float*>(b + 2 * up256(2 * px) + up256(px));
+    launch_resize_fwd(p.d, flow, mask, flow_s, mask_s, st);
+    p.flow = flow_s;
+    if (mask) p.mask = mask_s;
+    if (gflow && (rsz.on & 1)) p.gflow = gflow_s;
+    if (gmask && (rsz.on & 2)) p.gmask = gmask_s;
+    p.d.rs.on = 0;
+    rc = launch_bwd(p, lx, lg, b + front, workspace_bytes - front, st);
+    if (rc) return rc;
+    p.d.rs = rsz;
+    launch_resize_bwd(p.d, gflow_s, gmask_s, gflow, gmask, st);
+    return check_launch("c2m_warp_blend_bwd");
+  }
   rc = launch_bwd(p, lx, lg, workspace, workspace_bytes, st);
   if (rc) return rc;
   return check_launch("c2m_warp_blend_bwd");
+}
+
+int c2m_warp_blend_bwd(const float* x, const float* flow, const float* mask, const float* other, const float* gout,
+                       float* gx, float* gflow, float* gmask, float* gother, int64_t N, int C, int H, int W,
+                       int64_t x_batch, const int64_t x_strides[4], const int64_t g_strides[4], int padding,
+                       int flags, void* workspace, size_t workspace_bytes, void* cuda_stream) {
+  return c2m_warp_blend_bwd_rs(x, flow, mask, other, gout, gx, gflow, gmask, gother, N, C, H, W, x_batch, x_strides,
+                               g_strides, nullptr, padding, flags, workspace, workspace_bytes, cuda_stream);
 }
 
 int c2m_base_grid(float* grid, int64_t N, int H, int W, void* cuda_stream) {

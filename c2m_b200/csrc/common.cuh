@@ -20,6 +20,20 @@
 
 namespace c2m {
 
+// Bilinear resize of the flow / mask fused into the warp.  The reference resizes both to the
+// feature size right before every warp: generator.py:84-85,91-92 (F.interpolate bilinear, align_corners=False, flow
+// values NOT rescaled) and utils.py:346-354 + motion_autoencoder.py:120-124 (flow: align_corners=True, values
+// multiplied by new/old; mask: align_corners=False).  Arithmetic follows ATen's upsample_bilinear2d (UpSample.cuh
+// area_pixel_compute_scale / area_pixel_compute_source_index, UpSampleBilinear2d.cu upsample_bilinear2d_out_frame).
+struct Resize {
+  int on;          // bit 0: flow is given at (fh, fw) != (H, W); bit 1: mask is given at (mh, mw) != (H, W)
+  int fh, fw, mh, mw;
+  int f_align;     // flow: align_corners=True and value rescale (utils.py:346-354)
+  float fsy, fsx;  // flow: source-index scale (in-1)/(out-1) or in/out, float32 as ATen forms it
+  float msy, msx;  // mask: in/out
+  float fmulx, fmuly;  // flow value rescale: 1/(old/new) as a float32 reciprocal (ATen CUDA div-by-scalar), else 1
+};
+
 struct Dims {
   int N, C, H, W;
   int x_batch;  // distinct images in x (== N when there is no repeat)
@@ -27,6 +41,7 @@ struct Dims {
   float stepx, stepy;    // fp32 2/(n-1), as torch.linspace computes it
   float inv_bw, inv_bh;  // fp32 1/((n-1)/2)
   float bw, bh;          // fp32 (n-1)/2 (only for the TRUE_DIV probe variant)
+  Resize rs;
 };
 
 struct FwdParams {
@@ -80,6 +95,63 @@ struct BwdParams {
                             // and lists them as pixel | (s + 1) << 24 (tag 0: all channels, from segbin_kernel)
   float* gpart;             // channel-sliced gather (small levels): [slices][gflow N*2*HW | gmask N*HW] partial sums
 };
+
+// One output sample of ATen's upsample_bilinear2d: plane `pl` [Hs, Ws] sampled for output pixel (i, j).
+__device__ __forceinline__ void resize_taps(float scale, int dst, int in_size, bool align, int& i0, int& ip, float& l0,
+                                            float& l1) {
+  float r;
+  if (align) {
+    r = scale * (float)dst;
+  } else {
+    r = scale * ((float)dst + 0.5f) - 0.5f;
+    r = r < 0.f ? 0.f : r;
+  }
+  i0 = (int)r;
+  ip = (i0 < in_size - 1) ? 1 : 0;
+  l1 = r - (float)i0;
+  l0 = 1.f - l1;
+}
+__device__ __forceinline__ float bilerp_plane(const float* __restrict__ pl, int Hs, int Ws, float sy, float sx, bool align,
+                                              int i, int j) {
+  int h1, h1p, w1, w1p;
+  float h0l, h1l, w0l, w1l;
+  resize_taps(sy, i, Hs, align, h1, h1p, h0l, h1l);
+  resize_taps(sx, j, Ws, align, w1, w1p, w0l, w1l);
+  const float* r0 = pl + (int64_t)h1 * Ws + w1;
+  const float* r1 = r0 + (int64_t)h1p * Ws;
+  const float a = __ldg(r0), b = __ldg(r0 + w1p), c = __ldg(r1), e = __ldg(r1 + w1p);
+  // the expression of upsample_bilinear2d_out_frame, left to the compiler's default contraction as in ATen's build
+  return h0l * (w0l * a + w1l * b) + h1l * (w0l * c + w1l * e);
+}
+
+// flow (fx, fy) and mask value of output pixel (n, i, j): read directly, or resized on the fly from the tensors the
+// caller holds at another resolution.  `flow` / `mask` are the pointers as passed to the entry point.
+__device__ __forceinline__ void fetch_flow_mask(const Dims& d, const float* __restrict__ flow,
+                                                const float* __restrict__ mask, int n, int i, int j, float& fx, float& fy,
+                                                float& m) {
+  const Resize& rs = d.rs;
+  if (rs.on & 1) {
+    const float* f0 = flow + (int64_t)n * 2 * rs.fh * rs.fw;
+    fx = bilerp_plane(f0, rs.fh, rs.fw, rs.fsy, rs.fsx, rs.f_align != 0, i, j);
+    fy = bilerp_plane(f0 + (int64_t)rs.fh * rs.fw, rs.fh, rs.fw, rs.fsy, rs.fsx, rs.f_align != 0, i, j);
+    if (rs.f_align) {
+      fx = __fmul_rn(fx, rs.fmulx);
+      fy = __fmul_rn(fy, rs.fmuly);
+    }
+  } else {
+    const float* fl = flow + (int64_t)n * 2 * d.H * d.W + i * d.W + j;
+    fx = __ldg(fl);
+    fy = __ldg(fl + d.H * d.W);
+  }
+  if (mask) {
+    if (rs.on & 2)
+      m = bilerp_plane(mask + (int64_t)n * rs.mh * rs.mw, rs.mh, rs.mw, rs.msy, rs.msx, false, i, j);
+    else
+      m = __ldg(mask + (int64_t)n * d.H * d.W + i * d.W + j);
+  } else {
+    m = 1.f;
+  }
+}
 
 // Per-pixel sampling geometry, shared by forward and backward.
 struct Geo {
@@ -351,6 +423,12 @@ struct TileMaps {
 TileMaps make_tile_maps(const Dims& d, const float* flow, const float* mask, int TH, int TW);
 
 int launch_fwd(const FwdParams& p, Layout lx, Layout lo, cudaStream_t st);
+// fused-resize backward helpers (warp_resize.cu): materialise the resized flow / mask; back-propagate their gradients
+int fill_resize(Dims& d, const c2m_resize* rs);
+void launch_resize_fwd(const Dims& d, const float* flow_src, const float* mask_src, float* flow_out, float* mask_out,
+                       cudaStream_t st);
+void launch_resize_bwd(const Dims& d, const float* gflow_small, const float* gmask_small, float* gflow_src,
+                       float* gmask_src, cudaStream_t st);
 int launch_bwd(const BwdParams& p, Layout lx, Layout lg, void* workspace, size_t workspace_bytes, cudaStream_t st);
 size_t bwd_workspace_bytes(int64_t N, int C, int H, int W, int64_t x_batch, int want_gx, int flags);
 

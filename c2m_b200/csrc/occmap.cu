@@ -88,7 +88,10 @@ int c2m_occlusion_map(const float* in, float* out, int64_t N, int H, int W, int 
     return C2M_ERR_WORKSPACE;
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
-  if (cudaMemsetAsync(workspace, 0, need, st) != cudaSuccess) return C2M_ERR_CUDA;
+  if (cudaMemsetAsync(workspace, 0, need, st) != cudaSuccess) {
+    set_error("c2m_occlusion_map: cudaMemsetAsync: %s", cudaGetErrorString(cudaGetLastError()));
+    return C2M_ERR_CUDA;
+  }
   const int64_t total = N * H * W;
   int64_t blocks = (total + 255) / 256;
   const int64_t cap = (int64_t)sm_count() * 16;

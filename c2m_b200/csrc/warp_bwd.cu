@@ -286,7 +286,26 @@ static int launch_bwd_staged(const BwdParams& pin, void* workspace, size_t works
   return C2M_OK;
 }
 
+void launch_blend_other_bwd(const BwdParams& p, Layout lg, cudaStream_t st);
+
+int memset_failed() {
+  set_error("c2m_warp_blend_bwd: cudaMemsetAsync: %s", cudaGetErrorString(cudaGetLastError()));
+  return C2M_ERR_CUDA;
+}
+
 int launch_bwd(const BwdParams& pin, Layout lx, Layout lg, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  if ((pin.other || pin.gother) &&
+      !(pin.d.flags & (C2M_FLAG_FORCE_GENERIC | C2M_FLAG_BWD_ATOMIC | C2M_FLAG_COORD_GRID | C2M_FLAG_TRUE_DIV | C2M_FLAG_NO_FMA))) {
+    // blend operand: the fast kernels run as if `other` were absent (grad-mask = sum_c gout*warp), then one
+    // streaming pass writes grad-other = (1-m)*gout and subtracts sum_c gout*other from grad-mask
+    BwdParams q = pin;
+    q.other = nullptr;
+    q.gother = nullptr;
+    const int rc = launch_bwd(q, lx, lg, workspace, workspace_bytes, st);
+    if (rc) return rc;
+    if (pin.other && (pin.gmask || pin.gother)) launch_blend_other_bwd(pin, lg, st);
+    return C2M_OK;
+  }
   if ((pin.d.flags & C2M_FLAG_STAGE_NHWC) && lx == LAYOUT_NCHW && lg == LAYOUT_NCHW && workspace &&
       workspace_bytes >= bwd_workspace_bytes(pin.d.N, pin.d.C, pin.d.H, pin.d.W, pin.d.x_batch, pin.gx != nullptr,
                                              pin.d.flags) &&
@@ -319,11 +338,11 @@ int launch_bwd(const BwdParams& pin, Layout lx, Layout lg, void* workspace, size
     int64_t cnt = (int64_t)d.H * d.W * (d.N / d.x_batch);
     while ((1ll << (cl - 2)) < cnt) ++cl;
     p.count_log2 = cl;
-    if (cudaMemsetAsync(workspace, 0, 256 + (size_t)nx * sizeof(long long), st) != cudaSuccess) return C2M_ERR_CUDA;
+    if (cudaMemsetAsync(workspace, 0, 256 + (size_t)nx * sizeof(long long), st) != cudaSuccess) return memset_failed();
     absmax_kernel<<<grid_for(total), 256, 0, st>>>(p, maxbits);
     count_launch();
   } else if (p.gx) {
-    if (cudaMemsetAsync(p.gx, 0, (size_t)nx * sizeof(float), st) != cudaSuccess) return C2M_ERR_CUDA;
+    if (cudaMemsetAsync(p.gx, 0, (size_t)nx * sizeof(float), st) != cudaSuccess) return memset_failed();
   }
   const int grid = grid_for(total);
   if (det) {

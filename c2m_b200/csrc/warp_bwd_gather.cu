@@ -991,6 +991,7 @@ struct GatherWs {
 };
 
 static size_t up256(size_t v) { return (v + 255) & ~(size_t)255; }
+int memset_failed();  // warp_bwd.cu: sets the error text
 
 // global-list scheme (NCHW kernels)
 static GatherWs carve(void* base, int64_t N, int H, int W, int64_t x_batch) {
@@ -1265,7 +1266,7 @@ int launch_bwd_gather(const BwdParams& pin, Layout lx, void* workspace, size_t w
     p.ovf = w.ovf;
     p.ovf_count = w.ovf_count;
     p.ovf_list = w.ovf_list;
-    if (cudaMemsetAsync(w.tcnt, 0, w.clear_bytes, st) != cudaSuccess) return C2M_ERR_CUDA;
+    if (cudaMemsetAsync(w.tcnt, 0, w.clear_bytes, st) != cudaSuccess) return memset_failed();
     if (det) {
       // fixed-point scale from max|gout| * max|mask| (a bound of every |term|), accumulator rows cleared
       p.maxbits = w.maxbits;
@@ -1279,7 +1280,7 @@ int launch_bwd_gather(const BwdParams& pin, Layout lx, void* workspace, size_t w
       const int64_t cnt = (int64_t)d.H * d.W * (d.N / d.x_batch);
       while ((1ll << (cl - 2)) < cnt) ++cl;
       p.count_log2 = cl;
-      if (cudaMemsetAsync(w.maxbits, 0, w.det_clear_bytes, st) != cudaSuccess) return C2M_ERR_CUDA;
+      if (cudaMemsetAsync(w.maxbits, 0, w.det_clear_bytes, st) != cudaSuccess) return memset_failed();
       const int64_t ng = (int64_t)d.N * d.C * d.H * d.W;
       absmax_flat_kernel<<<sm_count() * 8, 256, 0, st>>>(p.gout, ng, w.maxbits);
       if (p.mask) absmax_flat_kernel<<<sm_count() * 2, 256, 0, st>>>(p.mask, (int64_t)d.N * d.H * d.W, w.maxbits + 1);
@@ -1307,7 +1308,7 @@ int launch_bwd_gather(const BwdParams& pin, Layout lx, void* workspace, size_t w
     p.ovf = w.ovf;
     p.ovf_count = w.ovf_count;
     p.ovf_list = w.ovf_list;
-    if (cudaMemsetAsync(p.cnt, 0, w.cnt_bytes, st) != cudaSuccess) return C2M_ERR_CUDA;
+    if (cudaMemsetAsync(p.cnt, 0, w.cnt_bytes, st) != cudaSuccess) return memset_failed();
     const int64_t total = (int64_t)d.N * d.H * d.W;
     bin_kernel<<<(unsigned)((total + kBinPixelsPerBlock - 1) / kBinPixelsPerBlock), 256, 0, st>>>(p);
     count_launch();

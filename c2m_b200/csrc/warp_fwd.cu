@@ -30,9 +30,15 @@ __global__ void __launch_bounds__(256) fwd_generic_kernel(const FwdParams p) {
     const int r = (int)(idx - (int64_t)n * HW);
     const int i = r / d.W, j = r - i * d.W;
     const bool gridmode = (d.flags & C2M_FLAG_COORD_GRID) != 0;
-    const float* fl = gridmode ? p.flow + ((int64_t)n * HW + r) * 2 : p.flow + (int64_t)n * 2 * HW + r;
-    const float fx = fl[0], fy = fl[gridmode ? 1 : HW];
-    const float m = p.mask ? p.mask[(int64_t)n * HW + r] : 1.f;
+    float fx, fy, m;
+    if (gridmode) {
+      const float* fl = p.flow + ((int64_t)n * HW + r) * 2;
+      fx = fl[0];
+      fy = fl[1];
+      m = p.mask ? p.mask[(int64_t)n * HW + r] : 1.f;
+    } else {
+      fetch_flow_mask(d, p.flow, p.mask, n, i, j, fx, fy, m);
+    }
     Geo g;
     make_geo<false, true>(d, fx, fy, i, j, g);
     const float* xb = p.x + (int64_t)(n % d.x_batch) * p.xs[0];
@@ -89,10 +95,7 @@ __global__ void __launch_bounds__(TH* TW, (TH * TW <= 256) ? 768 / (TH * TW) : 2
       fy = s.flow[buf][1][ty][tx];
       if (HAS_MASK) m = s.mask[buf][ty][tx];
     } else if (live) {
-      const float* fl = p.flow + (int64_t)n * 2 * HW + i * d.W + j;
-      fx = __ldg(fl);
-      fy = __ldg(fl + HW);
-      if (HAS_MASK) m = __ldg(p.mask + (int64_t)n * HW + i * d.W + j);
+      fetch_flow_mask(d, p.flow, HAS_MASK ? p.mask : nullptr, n, i, j, fx, fy, m);
     }
     if (live) {
       Geo g;
@@ -103,6 +106,9 @@ __global__ void __launch_bounds__(TH* TW, (TH * TW <= 256) ? 768 / (TH * TW) : 2
       const float* psw = xc + (g.y1 * d.W + g.x0);
       const float* pse = xc + (g.y1 * d.W + g.x1);
       float* oc = p.out + ((int64_t)n * d.C + c0) * HW + i * d.W + j;
+      // blend operand (out = m*warp + (1-m)*other): read at the output position, same strides as `out`
+      const float* otc = p.other ? p.other + ((int64_t)n * d.C + c0) * HW + i * d.W + j : nullptr;
+      const float om = 1.f - m;
 #pragma unroll UNROLL
       for (int c = 0; c < nc; ++c) {
         float vnw = __ldg(pnw), vne = __ldg(pne);
@@ -115,7 +121,12 @@ __global__ void __launch_bounds__(TH* TW, (TH * TW <= 256) ? 768 / (TH * TW) : 2
         acc = fmaf(vne, g.wne, acc);
         acc = fmaf(vsw, g.wsw, acc);
         acc = fmaf(vse, g.wse, acc);
-        st_stream(oc, HAS_MASK ? __fmul_rn(acc, m) : acc);
+        float o = HAS_MASK ? __fmul_rn(acc, m) : acc;
+        if (HAS_MASK && otc) {
+          o = __fadd_rn(o, __fmul_rn(om, __ldg(otc)));
+          otc += HW;
+        }
+        st_stream(oc, o);
         pnw += HW;
         pne += HW;
         psw += HW;
@@ -192,10 +203,7 @@ __global__ void __launch_bounds__(256, 6) fwd_nhwc_kernel(const __grid_constant_
     fy = s_flow[1][warp][lane];
     if (HAS_MASK) m = s_mask[warp][lane];
   } else if (live) {
-    const float* fl = p.flow + (int64_t)n * 2 * HW + i * d.W + j;
-    fx = __ldg(fl);
-    fy = __ldg(fl + HW);
-    if (HAS_MASK) m = __ldg(p.mask + (int64_t)n * HW + i * d.W + j);
+    fetch_flow_mask(d, p.flow, HAS_MASK ? p.mask : nullptr, n, i, j, fx, fy, m);
   }
   if (i >= d.H) return;  // whole warp
   const uint32_t pxb = (uint32_t)d.C * 4u;  // bytes per pixel
@@ -216,6 +224,8 @@ __global__ void __launch_bounds__(256, 6) fwd_nhwc_kernel(const __grid_constant_
   const uint32_t cb0 = blockIdx.y * (uint32_t)p.cchunk * 4u + lq * 16;
   const char* xl = reinterpret_cast<const char*>(p.x) + (int64_t)(n % d.x_batch) * HW * pxb + cb0;
   char* ol = reinterpret_cast<char*>(p.out) + ((int64_t)n * HW + (int64_t)i * d.W + bx * TW + grp) * pxb + cb0;
+  // blend operand (out = m*warp + (1-m)*other): the pixel's own row of `other`, same layout as `out`
+  const int64_t ot_delta = (HAS_MASK && p.other) ? reinterpret_cast<const char*>(p.other) - reinterpret_cast<const char*>(p.out) : 0;
   const int nq = QI > 0 ? QI : (C4 - lq + LP - 1) / LP;  // float4 groups of this lane
 #pragma unroll 1
   for (int s = 0; s < npx; s += G) {
@@ -250,6 +260,14 @@ __global__ void __launch_bounds__(256, 6) fwd_nhwc_kernel(const __grid_constant_
           o.y = __fmul_rn(o.y, mk.x);
           o.z = __fmul_rn(o.z, mk.x);
           o.w = __fmul_rn(o.w, mk.x);
+          if (ot_delta != 0) {
+            const float4 ot = ldg_batch(reinterpret_cast<const float4*>(po + ot_delta));
+            const float om = 1.f - mk.x;
+            o.x = __fadd_rn(o.x, __fmul_rn(om, ot.x));
+            o.y = __fadd_rn(o.y, __fmul_rn(om, ot.y));
+            o.z = __fadd_rn(o.z, __fmul_rn(om, ot.z));
+            o.w = __fadd_rn(o.w, __fmul_rn(om, ot.w));
+          }
         }
         st_stream(reinterpret_cast<float4*>(po), o);
         px += LP * 16;
@@ -266,7 +284,9 @@ __global__ void __launch_bounds__(256, 6) fwd_nhwc_kernel(const __grid_constant_
 TileMaps make_tile_maps(const Dims& d, const float* flow, const float* mask, int TH, int TW) {
   TileMaps m;
   memset(&m, 0, sizeof(m));
-  m.ok = !(d.flags & C2M_FLAG_NO_TMA) && make_tensor_map_3d(&m.flow, flow, d.W, d.H, (int64_t)d.N * 2, TW, TH, 2);
+  // (a flow / mask that is resized on the fly has no tile to fetch: plain loads through fetch_flow_mask)
+  m.ok = !(d.flags & C2M_FLAG_NO_TMA) && !d.rs.on &&
+         make_tensor_map_3d(&m.flow, flow, d.W, d.H, (int64_t)d.N * 2, TW, TH, 2);
   if (m.ok && mask) m.ok = make_tensor_map_3d(&m.mask, mask, d.W, d.H, d.N, TW, TH, 1);
   return m;
 }
@@ -355,8 +375,7 @@ int launch_fwd(const FwdParams& p, Layout lx, Layout lo, cudaStream_t st) {
 static int launch_fwd_impl(const FwdParams& p, Layout lx, Layout lo, cudaStream_t st) {
   const Dims& d = p.d;
   const bool generic = (d.flags & (C2M_FLAG_FORCE_GENERIC | C2M_FLAG_COORD_GRID | C2M_FLAG_TRUE_DIV | C2M_FLAG_NO_FMA)) ||
-                       p.other != nullptr || lx != lo ||
-                       lx == LAYOUT_OTHER || (int64_t)d.H * d.W >= (1ll << 30);
+                       lx != lo || lx == LAYOUT_OTHER || (int64_t)d.H * d.W >= (1ll << 30);
   if (!generic && lx == LAYOUT_NCHW) {
     const int variant = (d.flags >> 16) & 0xf;  // tuning hook (bench sweeps); 0 = default
     switch (variant) {
@@ -370,6 +389,7 @@ static int launch_fwd_impl(const FwdParams& p, Layout lx, Layout lo, cudaStream_
   }
   // the channels-last kernel addresses corners by 32-bit byte offsets inside one image
   if (!generic && lx == LAYOUT_NHWC && (d.C % 4) == 0 && ((uintptr_t)p.x % 16) == 0 && ((uintptr_t)p.out % 16) == 0 &&
+      ((uintptr_t)p.other % 16) == 0 &&
       (int64_t)d.H * d.W * d.C < (1ll << 30))
     return launch_nhwc(p, st);
   const int64_t total = (int64_t)d.N * d.H * d.W;

@@ -232,7 +232,10 @@ int c2m_warped_l1_bwd(const float* source, const float* flows, const float* targ
   if (p.total == 0 || (!gflows && !gtargets)) return C2M_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
   if (C == 0) {  // no channels: the flows' gradient is zero (the loss itself is NaN)
-    if (gflows && cudaMemsetAsync(gflows, 0, (size_t)p.total * 2 * sizeof(float), st) != cudaSuccess) return C2M_ERR_CUDA;
+    if (gflows && cudaMemsetAsync(gflows, 0, (size_t)p.total * 2 * sizeof(float), st) != cudaSuccess) {
+      set_error("c2m_warped_l1_bwd: cudaMemsetAsync: %s", cudaGetErrorString(cudaGetLastError()));
+      return C2M_ERR_CUDA;
+    }
     return C2M_OK;
   }
   if (!source || !flows || !targets || !gloss) {

@@ -54,7 +54,44 @@ def _dense(t: torch.Tensor, nhwc: bool) -> torch.Tensor:
     return t.contiguous(memory_format=torch.channels_last) if nhwc else t.contiguous()
 
 
-def _check_inputs(x, flow, mask, other):
+_RESIZE_MODES = {"half_pixel": _lib.RESIZE_HALF_PIXEL, "corners_rescaled": _lib.RESIZE_CORNERS_RESCALE}
+
+# NCHW tensors are staged through channels-last copies in the backward workspace (three tensor-sized buffers) only
+# while those copies stay below this many bytes; larger calls run the NCHW kernels (slower, no extra memory).
+_STAGE_MAX_BYTES = int(os.environ.get("C2M_WARP_STAGE_MAX_BYTES", str(8 << 30)))
+# Backward workspaces up to this size are kept per (device, stream) and reused by later calls on that stream (stream
+# order makes that safe); larger ones come from torch's caching allocator per call.
+_WS_CACHE_MAX_BYTES = int(os.environ.get("C2M_WARP_WS_CACHE_BYTES", str(64 << 20)))
+_ws_cache = {}
+
+
+def _workspace(nbytes: int, device: torch.device, stream) -> torch.Tensor:
+    if nbytes > _WS_CACHE_MAX_BYTES or torch.cuda.is_current_stream_capturing():
+        # (a buffer captured into a CUDA graph must not be recycled by later eager calls)
+        return torch.empty(nbytes, dtype=torch.uint8, device=device)
+    key = (device.index, stream)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+def _resize_spec(x, flow, mask, flow_resize):
+    """c2m_resize for a flow / mask held at another resolution than x (None: same size)."""
+    H, W = x.shape[2:]
+    fh, fw = flow.shape[2:]
+    mh, mw = (mask.shape[2:] if mask is not None else (H, W))
+    if (fh, fw) == (H, W) and (mh, mw) == (H, W):
+        return None
+    if (fh, fw) != (H, W) and flow_resize is None:
+        raise ValueError(f"flow {tuple(flow.shape)} does not match x {tuple(x.shape)} spatially "
+                         "(pass flow_resize='half_pixel' or 'corners_rescaled' to resize it inside the kernel)")
+    mode = _RESIZE_MODES[flow_resize or "half_pixel"]
+    return _lib.resize_spec(fh, fw, mh, mw, mode)
+
+
+def _check_inputs(x, flow, mask, other, resized=False):
     for name, t in (("x", x), ("flow", flow), ("mask", mask), ("other", other)):
         if t is None:
             continue
@@ -67,14 +104,20 @@ def _check_inputs(x, flow, mask, other):
             raise RuntimeError("c2m_b200.warp_blend: all tensors must be on the same device")
     if x.dim() != 4 or flow.dim() != 4 or flow.shape[1] != 2:
         raise ValueError(f"expected x [B,C,H,W] and flow [N,2,H,W], got {tuple(x.shape)} and {tuple(flow.shape)}")
-    N, _, H, W = flow.shape
-    if tuple(x.shape[2:]) != (H, W):
-        raise ValueError(f"flow {tuple(flow.shape)} does not match x {tuple(x.shape)} spatially")
+    N = flow.shape[0]
+    H, W = x.shape[2:]
     B = x.shape[0]
     if B != N and (B == 0 or N % B != 0):
         raise ValueError(f"x batch {B} must equal or divide the flow batch {N}")
-    if mask is not None and tuple(mask.shape) != (N, 1, H, W):
-        raise ValueError(f"mask must be [N,1,H,W]={N, 1, H, W}, got {tuple(mask.shape)}")
+    if mask is not None and (mask.dim() != 4 or mask.shape[0] != N or mask.shape[1] != 1):
+        raise ValueError(f"mask must be [N,1,h,w] with N={N}, got {tuple(mask.shape)}")
+    if not resized:
+        if tuple(flow.shape[2:]) != (H, W):
+            raise ValueError(f"flow {tuple(flow.shape)} does not match x {tuple(x.shape)} spatially")
+        if mask is not None and tuple(mask.shape) != (N, 1, H, W):
+            raise ValueError(f"mask must be [N,1,H,W]={N, 1, H, W}, got {tuple(mask.shape)}")
+    elif min(flow.shape[2:]) == 0 or (mask is not None and min(mask.shape[2:]) == 0):
+        raise ValueError("cannot resize an empty flow / mask")
     if other is not None:
         if mask is None:
             raise ValueError("`other` requires a mask")
@@ -89,23 +132,27 @@ class WarpBlendFunction(torch.autograd.Function):
     # native warp (src/modules/third_party/resample2d/resample2d.py:55-57: autocast(False) + .float())
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
-    def forward(ctx, x, flow, mask, other, padding, deterministic, flags):
-        _check_inputs(x, flow, mask, other)
+    def forward(ctx, x, flow, mask, other, padding, deterministic, flags, flow_resize=None):
+        if x.dim() != 4 or flow.dim() != 4:
+            raise ValueError(f"expected x [B,C,H,W] and flow [N,2,h,w], got {tuple(x.shape)} and {tuple(flow.shape)}")
+        rs = _resize_spec(x, flow, mask, flow_resize)
+        _check_inputs(x, flow, mask, other, resized=rs is not None)
         nhwc = _is_nhwc_dense(x)
         x = _dense(x, nhwc)
         flow = flow.contiguous()
         mask = None if mask is None else mask.contiguous()
         other = None if other is None else _dense(other, nhwc)
-        N, _, H, W = flow.shape
+        N = flow.shape[0]
+        H, W = x.shape[2:]
         B, C = x.shape[0], x.shape[1]
         out = torch.empty((N, C, H, W), dtype=x.dtype, device=x.device,
                           memory_format=torch.channels_last if nhwc else torch.contiguous_format)
         with _on_device(x.device):
             stream = torch.cuda.current_stream().cuda_stream
             _lib.warp_blend_fwd(_ptr(x), _ptr(flow), _ptr(mask), _ptr(other), _ptr(out), N, C, H, W, B,
-                                x.stride(), out.stride(), padding, flags, stream)
+                                x.stride(), out.stride(), padding, flags, stream, rs)
         ctx.save_for_backward(x, flow, mask, other)  # inputs only: geometry is recomputed in backward
-        ctx.cfg = (padding, bool(deterministic), flags, nhwc)
+        ctx.cfg = (padding, bool(deterministic), flags, nhwc, rs)
         return out
 
     @staticmethod
@@ -113,12 +160,13 @@ class WarpBlendFunction(torch.autograd.Function):
     @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, gout):
         x, flow, mask, other = ctx.saved_tensors
-        padding, deterministic, flags, nhwc = ctx.cfg
+        padding, deterministic, flags, nhwc, rs = ctx.cfg
         need_x, need_flow, need_mask, need_other = ctx.needs_input_grad[:4]
         need_mask = need_mask and mask is not None
         need_other = need_other and other is not None
         gout = _dense(gout, nhwc)
-        N, _, H, W = flow.shape
+        N = flow.shape[0]
+        H, W = x.shape[2:]
         B, C = x.shape[0], x.shape[1]
         gx = torch.empty_like(x) if need_x else None
         gflow = torch.empty_like(flow) if need_flow else None
@@ -126,21 +174,23 @@ class WarpBlendFunction(torch.autograd.Function):
         gother = torch.empty_like(gout) if need_other else None
         if deterministic:
             flags |= _lib.FLAG_DETERMINISTIC
-        if not nhwc and need_x and C % 4 == 0 and not (flags & _lib.FLAG_NO_STAGE):
+        if (not nhwc and need_x and C % 4 == 0 and not (flags & _lib.FLAG_NO_STAGE)
+                and 4 * (N + 2 * B) * C * H * W <= _STAGE_MAX_BYTES):
             # NCHW tensors: the library stages them through channels-last copies in the workspace and runs
-            # the channels-last kernels (about twice as fast as gathering 4-byte elements at NCHW strides)
+            # the channels-last kernels (about twice as fast as gathering 4-byte elements at NCHW strides);
+            # C2M_WARP_STAGE_MAX_BYTES bounds the extra footprint
             flags |= _lib.FLAG_STAGE_NHWC
         with _on_device(x.device):
-            ws_bytes = _lib.bwd_workspace_bytes(N, C, H, W, B, need_x, flags)
-            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
             stream = torch.cuda.current_stream().cuda_stream
+            ws_bytes = _lib.bwd_workspace_bytes(N, C, H, W, B, need_x, flags, rs)
+            ws = _workspace(ws_bytes, x.device, stream)
             _lib.warp_blend_bwd(_ptr(x), _ptr(flow), _ptr(mask), _ptr(other), _ptr(gout), _ptr(gx), _ptr(gflow),
                                 _ptr(gmask), _ptr(gother), N, C, H, W, B, x.stride(), gout.stride(), padding,
-                                flags, _ptr(ws), ws_bytes, stream)
-        return gx, gflow, gmask, gother, None, None, None
+                                flags, _ptr(ws), ws_bytes, stream, rs)
+        return gx, gflow, gmask, gother, None, None, None, None
 
 
-def warp_blend(x, flow, mask=None, other=None, padding="border", deterministic=None, flags=0):
+def warp_blend(x, flow, mask=None, other=None, padding="border", deterministic=None, flags=0, flow_resize=None):
     """Fused ``resample(x, flow) * mask`` of the reference (ops.py:187-193, generator.py:93).
 
     x      [B,C,H,W] float32 CUDA, NCHW-contiguous or channels-last (output follows x's format);
@@ -149,7 +199,12 @@ def warp_blend(x, flow, mask=None, other=None, padding="border", deterministic=N
     flow   [N,2,H,W] displacement in pixels, channel 0 = x.
     mask   [N,1,H,W] or None (None: plain warp, generator.py:95-96).
     other  optional [N,C,H,W]: out = mask*warp + (1-mask)*other (not in the reference).
+    flow_resize  flow [N,2,h,w] / mask [N,1,h',w'] held at another resolution than x are resized to (H, W) inside
+           the kernel (bilinear; the gradients come back at their own sizes): "half_pixel" = generator.py:84-85
+           (align_corners=False, values kept), "corners_rescaled" = utils.py:346-354 (align_corners=True, values
+           scaled by new/old).  The mask is always resized with align_corners=False (generator.py:92).
     """
     if deterministic is None:
         deterministic = deterministic_default()
-    return WarpBlendFunction.apply(x, flow, mask, other, _PADDING[padding], bool(deterministic), int(flags))
+    return WarpBlendFunction.apply(x, flow, mask, other, _PADDING[padding], bool(deterministic), int(flags),
+                                   flow_resize)

@@ -20,31 +20,19 @@ from .functional import warp_blend
 from .ops import get_corresponding_map, get_grid, get_occlusion_map, grid_sample, resample
 
 
-def _flow_for(inp: torch.Tensor, optical_flow: torch.Tensor) -> torch.Tensor:
-    """generator.py:82-85.  The reference unpacks the NCHW flow as NHWC and therefore always sends
-    it through F.interpolate(bilinear, align_corners=False) without rescaling the values; when the
-    sizes already match that resize is the identity bit for bit, so
-    it is skipped here."""
-    h, w = inp.shape[2:]
-    if optical_flow.shape[2] != h or optical_flow.shape[3] != w:
-        optical_flow = F.interpolate(optical_flow, size=(h, w), mode="bilinear")
-    return optical_flow
-
-
 def deform_input(inp: torch.Tensor, optical_flow: torch.Tensor) -> torch.Tensor:
-    """Same contract as OcclusionAwareGenerator.deform_input (a staticmethod in the reference)."""
-    return resample(inp, _flow_for(inp, optical_flow))
+    """Same contract as OcclusionAwareGenerator.deform_input (a staticmethod in the reference, generator.py:80-86).
+    The reference unpacks the NCHW flow as NHWC and therefore always sends it through F.interpolate(bilinear,
+    align_corners=False) without rescaling the values; when the sizes already match that resize is the identity bit
+    for bit.  Here the resize happens inside the warp kernel (one launch)."""
+    return warp_blend(inp, optical_flow, None, flow_resize="half_pixel")
 
 
 def apply_optical(self=None, input_ref=None, optical_flow=None, occlusion_map=None):
-    """Same contract as OcclusionAwareGenerator.apply_optical: warp `input_ref` by the flow and
-    multiply by the occlusion map (resized with bilinear/align_corners=False when its size
-    differs).  The warp and the multiply are one kernel; forward saves only the inputs."""
-    flow = _flow_for(input_ref, optical_flow)
-    if occlusion_map is not None:
-        if input_ref.shape[2] != occlusion_map.shape[2] or input_ref.shape[3] != occlusion_map.shape[3]:
-            occlusion_map = F.interpolate(occlusion_map, size=input_ref.shape[2:], mode="bilinear")
-    return warp_blend(input_ref, flow, occlusion_map)
+    """Same contract as OcclusionAwareGenerator.apply_optical (generator.py:88-96): warp `input_ref` by the flow and
+    multiply by the occlusion map, both resized to the feature size with bilinear / align_corners=False when their
+    sizes differ.  Resize, warp and multiply are ONE kernel; forward saves only the inputs (at their own sizes)."""
+    return warp_blend(input_ref, optical_flow, occlusion_map, flow_resize="half_pixel")
 
 
 def resize_flow(flow: torch.Tensor, new_shape) -> torch.Tensor:
@@ -60,14 +48,14 @@ def resize_flow(flow: torch.Tensor, new_shape) -> torch.Tensor:
 def decoder_warp(app_features: torch.Tensor, sparse_motion: torch.Tensor, sparse_occlusion: torch.Tensor,
                  num_frames: int) -> torch.Tensor:
     """One scale of DenseMotionDecoder.forward (motion_autoencoder.py:117-125).  The reference
-    materialises T copies of the appearance map folded into the batch (t-major) before warping;
-    here the kernel reads image n % B instead, so the features are read, and their gradient is
+    materialises T copies of the appearance map folded into the batch (t-major) before warping, resizes the
+    motion with `resize_flow` (align_corners=True, values rescaled) and the occlusion with F.interpolate; here the
+    kernel reads image n % B and resizes both on the fly, so the features are read, and their gradient is
     accumulated, in place.  sparse_motion [B,2,T,H,W], sparse_occlusion [B,1,T,H,W]."""
-    nh, nw = app_features.shape[-2:]
-    motion = resize_flow(torch.cat(torch.unbind(sparse_motion, 2), 0), [nh, nw])
-    occ = F.interpolate(torch.cat(torch.unbind(sparse_occlusion, 2), 0), size=[nh, nw], mode="bilinear")
+    motion = torch.cat(torch.unbind(sparse_motion, 2), 0)
+    occ = torch.cat(torch.unbind(sparse_occlusion, 2), 0)
     assert motion.shape[0] == app_features.shape[0] * num_frames
-    return warp_blend(app_features, motion, occ)
+    return warp_blend(app_features, motion, occ, flow_resize="corners_rescaled")
 
 
 _PATCH_TARGETS = (

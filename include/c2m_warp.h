@@ -30,7 +30,8 @@
  *     generic kernel); flow is [N, 2, H, W] contiguous, channel 0 = x displacement in pixels;
  *     mask is [N, 1, H, W] contiguous or NULL;
  *   - `other` NULL  => out = mask * warp(x)                       (reference semantics)
- *     `other` given => out = mask * warp(x) + (1 - mask) * other  (north-star blend, needs mask);
+ *     `other` given => out = mask * warp(x) + (1 - mask) * other  (north-star blend, needs mask); `other` has the
+ *     output's strides (out_strides in the forward, g_strides in the backward, like gother);
  *   - x_batch: number of distinct images in x. x_batch == N (or 0) is the plain case. x_batch < N
  *     (N % x_batch == 0) means frame n reads image n % x_batch, i.e. the T-fold repeat of
  *     motion_autoencoder.py:117-119 without materialising the copies; gx is then [x_batch,C,H,W]
@@ -55,7 +56,7 @@ extern "C" {
 #define C2M_API
 #endif
 
-#define C2M_WARP_VERSION 100
+#define C2M_WARP_VERSION 200
 
 /* padding (ATen GridSamplerPadding): the reference path uses border (ops.py:184); zeros is the
  * flavour of src/modules/motion_estimator/dense_motion.py:167 */
@@ -102,6 +103,38 @@ C2M_API int c2m_warp_blend_bwd(const float* x, const float* flow, const float* m
 
 C2M_API size_t c2m_warp_bwd_workspace_bytes(int64_t N, int C, int H, int W, int64_t x_batch, int want_gx,
                                     int flags);
+
+/* The same op with the bilinear resize of the flow and the mask fused in.  The reference resizes
+ * both to the feature size right before every warp:
+ *   C2M_RESIZE_HALF_PIXEL       src/modules/generator/generator.py:84-85,91-92 -- F.interpolate(bilinear), i.e.
+ *                               align_corners=False, flow VALUES NOT rescaled;
+ *   C2M_RESIZE_CORNERS_RESCALE  src/utils/utils.py:346-354 `resize_flow` (+ motion_autoencoder.py:120-124) --
+ *                               align_corners=True, flow x / y values divided by old_w/new_w and old_h/new_h.
+ * The mask is always resized with align_corners=False (generator.py:92, motion_autoencoder.py:122-124).
+ * `flow` is [N,2,flow_h,flow_w], `mask` [N,1,mask_h,mask_w] (0 = the feature size H, W: no resize of that tensor).
+ * Forward: one launch, the taps are gathered inside the warp kernel.  Backward: gflow / gmask have the shapes of
+ * flow / mask as passed (the gradient is taken through the resize: ATen upsample_bilinear2d_backward + the divides),
+ * written in full, bitwise reproducible (a gather over source pixels, no atomics).  rs == NULL: same as the calls above. */
+#define C2M_RESIZE_HALF_PIXEL 0
+#define C2M_RESIZE_CORNERS_RESCALE 1
+typedef struct c2m_resize {
+  int flow_h, flow_w; /* size of `flow` as passed; 0 = H, W */
+  int mask_h, mask_w; /* size of `mask` as passed; 0 = H, W */
+  int flow_mode;      /* C2M_RESIZE_* (ignored when the flow is not resized) */
+} c2m_resize;
+
+C2M_API int c2m_warp_blend_fwd_rs(const float* x, const float* flow, const float* mask, const float* other,
+                                  float* out, int64_t N, int C, int H, int W, int64_t x_batch,
+                                  const int64_t x_strides[4], const int64_t out_strides[4], const c2m_resize* rs,
+                                  int padding, int flags, void* cuda_stream);
+C2M_API int c2m_warp_blend_bwd_rs(const float* x, const float* flow, const float* mask, const float* other,
+                                  const float* gout, float* gx, float* gflow, float* gmask, float* gother,
+                                  int64_t N, int C, int H, int W, int64_t x_batch,
+                                  const int64_t x_strides[4], const int64_t g_strides[4], const c2m_resize* rs,
+                                  int padding, int flags, void* workspace, size_t workspace_bytes,
+                                  void* cuda_stream);
+C2M_API size_t c2m_warp_bwd_workspace_bytes_rs(int64_t N, int C, int H, int W, int64_t x_batch, int want_gx,
+                                               const c2m_resize* rs, int flags);
 
 /* [N,2,H,W] base grid, bit-identical to the reference's CPU float32 construction. */
 C2M_API int c2m_base_grid(float* grid, int64_t N, int H, int W, void* cuda_stream);

@@ -86,3 +86,8 @@ a = graphed(fused)
 print(f"  fused, CUDA-graph replay          {a:8.3f} ms   ({by / a / 1e6:7.1f} GB/s)")
 print(f"  T x c2m_b200.resample + l1_loss   {timed(ours_loop):8.3f} ms")
 print(f"  reference torch composition       {timed(torch_loop, 5):8.3f} ms")
+# (a process that exits right after a backward can meet PyTorch's autograd worker thread still releasing the last
+# graph's tensors while the interpreter finalises -- PyEval_AcquireThread -> pthread_exit -> std::terminate, seen on
+# the GPU boxes with a native backtrace, tools/diag/term_trace.cpp; give that thread a moment)
+torch.cuda.synchronize()
+time.sleep(0.2)

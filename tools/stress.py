@@ -82,6 +82,10 @@ def main(iters, seed):
             print("MISS", it, dict(N=N, B=B, C=C, H=H, W=W, kind=kind, det=det, cl=not x.is_contiguous(), mask=mask is not None), errs)
             return 1
     print("ok", iters, "cases; worst", {k: float("%.2e" % v) for k, v in worst.items()})
+    # the autograd worker thread may still be releasing the last graph's tensors: see tools/bench_loss_site.py
+    torch.cuda.synchronize()
+    import time
+    time.sleep(0.2)
     return 0
 
 
