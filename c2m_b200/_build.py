@@ -11,7 +11,7 @@ import subprocess
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libc2m_warp.so")
-SOURCES = ["api.cu", "warp_fwd.cu", "warp_bwd.cu", "warp_bwd_gather.cu", "warp_aux.cu", "occmap.cu", "warped_l1.cu"]
+SOURCES = ["api.cu", "warp_fwd.cu", "warp_bwd.cu", "warp_bwd_gather.cu", "warp_aux.cu", "affine_warp.cu", "occmap.cu", "warped_l1.cu", "flowcon.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",

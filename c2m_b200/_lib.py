@@ -42,9 +42,14 @@ SYMBOLS = (
     "c2m_occlusion_map_workspace_bytes",
     "c2m_warp_profile",
     "c2m_warp_profile_last_ms",
+    "c2m_affine_warp",
+    "c2m_sparse_motion",
     "c2m_warped_l1_workspace_bytes",
     "c2m_warped_l1_fwd",
     "c2m_warped_l1_bwd",
+    "c2m_flow_consistency_workspace_bytes",
+    "c2m_flow_consistency_fwd",
+    "c2m_flow_consistency_bwd",
 )
 
 _lock = threading.Lock()
@@ -122,6 +127,10 @@ def load(build_if_missing: bool = False) -> ctypes.CDLL:
         lib.c2m_occlusion_map_workspace_bytes.argtypes = [_i64, _int, _int]
         lib.c2m_occlusion_map.restype = _int
         lib.c2m_occlusion_map.argtypes = [_ptr, _ptr, _i64, _int, _int, _int, _ptr, ctypes.c_size_t, _ptr]
+        lib.c2m_affine_warp.restype = _int
+        lib.c2m_affine_warp.argtypes = [_ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i64, _int, _int, _int, _ptr]
+        lib.c2m_sparse_motion.restype = _int
+        lib.c2m_sparse_motion.argtypes = [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _int, _int, _int, _int, _ptr]
         lib.c2m_warped_l1_workspace_bytes.restype = ctypes.c_size_t
         lib.c2m_warped_l1_workspace_bytes.argtypes = []
         lib.c2m_warped_l1_fwd.restype = _int
@@ -129,6 +138,14 @@ def load(build_if_missing: bool = False) -> ctypes.CDLL:
                                           _ptr]
         lib.c2m_warped_l1_bwd.restype = _int
         lib.c2m_warped_l1_bwd.argtypes = [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _int, _int, _int, _int, _ptr]
+        lib.c2m_flow_consistency_workspace_bytes.restype = ctypes.c_size_t
+        lib.c2m_flow_consistency_workspace_bytes.argtypes = [_i64, _int, _int, _int]
+        lib.c2m_flow_consistency_fwd.restype = _int
+        lib.c2m_flow_consistency_fwd.argtypes = [_ptr, _ptr, _ptr, _ptr, _ptr, _i64, _int, _int, _int, ctypes.c_float,
+                                                 _ptr, ctypes.c_size_t, _ptr]
+        lib.c2m_flow_consistency_bwd.restype = _int
+        lib.c2m_flow_consistency_bwd.argtypes = [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _int, _int,
+                                                 _int, ctypes.c_float, _ptr, ctypes.c_size_t, _ptr]
         _lib = lib
     return _lib
 
@@ -199,6 +216,16 @@ def occlusion_map_workspace_bytes(N, H, W) -> int:
     return int(load().c2m_occlusion_map_workspace_bytes(N, H, W))
 
 
+def affine_warp(theta_ptr, x_ptr, x_index_ptr, tx_ptr, flow_ptr, K, Kx, C, H, W, stream) -> None:
+    _check(load().c2m_affine_warp(theta_ptr, x_ptr, x_index_ptr, tx_ptr, flow_ptr, K, Kx, C, H, W, stream),
+           "c2m_affine_warp")
+
+
+def sparse_motion(inst_ptr, ids_ptr, batch_ptr, thetas_ptr, bw_ptr, fw_ptr, bin_ptr, B, T, H, W, n_obj, stream) -> None:
+    _check(load().c2m_sparse_motion(inst_ptr, ids_ptr, batch_ptr, thetas_ptr, bw_ptr, fw_ptr, bin_ptr, B, T, H, W,
+                                    n_obj, stream), "c2m_sparse_motion")
+
+
 def warped_l1_workspace_bytes() -> int:
     return int(load().c2m_warped_l1_workspace_bytes())
 
@@ -211,6 +238,23 @@ def warped_l1_fwd(src_ptr, flows_ptr, tgt_ptr, loss_ptr, B, C, T, H, W, ws_ptr, 
 def warped_l1_bwd(src_ptr, flows_ptr, tgt_ptr, gloss_ptr, gflows_ptr, gtargets_ptr, B, C, T, H, W, stream) -> None:
     _check(load().c2m_warped_l1_bwd(src_ptr, flows_ptr, tgt_ptr, gloss_ptr, gflows_ptr, gtargets_ptr, B, C, T, H, W,
                                     stream), "c2m_warped_l1_bwd")
+
+
+def flow_consistency_workspace_bytes(B, T, H, W) -> int:
+    return int(load().c2m_flow_consistency_workspace_bytes(B, T, H, W))
+
+
+def flow_consistency_fwd(flow_ptr, back_ptr, mfw_ptr, mbw_ptr, loss_ptr, B, T, H, W, scale, ws_ptr, ws_bytes,
+                         stream) -> None:
+    _check(load().c2m_flow_consistency_fwd(flow_ptr, back_ptr, mfw_ptr, mbw_ptr, loss_ptr, B, T, H, W, scale, ws_ptr,
+                                           ws_bytes, stream), "c2m_flow_consistency_fwd")
+
+
+def flow_consistency_bwd(flow_ptr, back_ptr, mfw_ptr, mbw_ptr, gloss_ptr, gflow_ptr, gback_ptr, gmfw_ptr, gmbw_ptr,
+                         B, T, H, W, scale, ws_ptr, ws_bytes, stream) -> None:
+    _check(load().c2m_flow_consistency_bwd(flow_ptr, back_ptr, mfw_ptr, mbw_ptr, gloss_ptr, gflow_ptr, gback_ptr,
+                                           gmfw_ptr, gmbw_ptr, B, T, H, W, scale, ws_ptr, ws_bytes, stream),
+           "c2m_flow_consistency_bwd")
 
 
 def profile(enable: bool) -> None:

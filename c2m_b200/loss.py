@@ -17,7 +17,7 @@ from torch.autograd.function import once_differentiable
 from . import _lib
 from .functional import warp_blend
 
-__all__ = ["warped_l1_loss", "WarpedL1Function"]
+__all__ = ["warped_l1_loss", "WarpedL1Function", "flow_consistency_loss", "FlowConsistencyFunction", "FlowConsistLoss"]
 
 
 class WarpedL1Function(torch.autograd.Function):
@@ -89,3 +89,86 @@ def warped_l1_loss(source: torch.Tensor, flows: torch.Tensor, targets: torch.Ten
         warped = warp_blend(source, flows.permute(2, 0, 1, 3, 4).reshape(T * B, 2, H, W), None)
         return F.l1_loss(warped.view(T, B, C, H, W).permute(1, 2, 0, 3, 4), targets)
     return WarpedL1Function.apply(source, flows, targets)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Flow-consistency loss (losses.py:115-141)
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+class FlowConsistencyFunction(torch.autograd.Function):
+    """scale * (mean(mask_bw*|resample(flow, flowback) + flowback|) + mean(mask_fw*|resample(flowback, flow) + flow|))
+    on the 5-D tensors as they are; gradients for both flows and both masks."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, flow, flowback, mask_fw, mask_bw, scale):
+        flow, flowback = flow.contiguous(), flowback.contiguous()
+        mask_fw = None if mask_fw is None else mask_fw.contiguous()
+        mask_bw = None if mask_bw is None else mask_bw.contiguous()
+        B, _, T, H, W = flow.shape
+        loss = torch.empty((), dtype=torch.float32, device=flow.device)
+        with torch.cuda.device(flow.device):
+            ws_bytes = _lib.flow_consistency_workspace_bytes(B, T, H, W)
+            ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=flow.device)
+            _lib.flow_consistency_fwd(flow.data_ptr(), flowback.data_ptr(), _p(mask_fw), _p(mask_bw), loss.data_ptr(),
+                                      B, T, H, W, float(scale), ws.data_ptr(), ws_bytes,
+                                      torch.cuda.current_stream().cuda_stream)
+        ctx.save_for_backward(flow, flowback, mask_fw, mask_bw)
+        ctx.scale = float(scale)
+        return loss
+
+    @staticmethod
+    @once_differentiable
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, gloss):
+        flow, flowback, mask_fw, mask_bw = ctx.saved_tensors
+        B, _, T, H, W = flow.shape
+        need = ctx.needs_input_grad
+        gloss = gloss.to(torch.float32).contiguous()
+        gflow = torch.empty_like(flow) if need[0] else None
+        gback = torch.empty_like(flowback) if need[1] else None
+        gmfw = torch.empty_like(mask_fw) if (need[2] and mask_fw is not None) else None
+        gmbw = torch.empty_like(mask_bw) if (need[3] and mask_bw is not None) else None
+        with torch.cuda.device(flow.device):
+            ws_bytes = _lib.flow_consistency_workspace_bytes(B, T, H, W)
+            ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=flow.device)
+            _lib.flow_consistency_bwd(flow.data_ptr(), flowback.data_ptr(), _p(mask_fw), _p(mask_bw), gloss.data_ptr(),
+                                      _p(gflow), _p(gback), _p(gmfw), _p(gmbw), B, T, H, W, ctx.scale, ws.data_ptr(),
+                                      ws_bytes, torch.cuda.current_stream().cuda_stream)
+        return gflow, gback, gmfw, gmbw, None
+
+
+def flow_consistency_loss(flow, flowback, mask_fw=None, mask_bw=None, num_predicted_frames=None):
+    """`FlowConsistLoss.forward` (losses.py:131-141).  flow / flowback [B,2,T,H,W] in pixels, masks [B,1,T,H,W] or
+    None (the reference tests `mask_bw is not None` and then uses both).  The result is multiplied by
+    `num_predicted_frames` (default: T, the value the shipped YAML makes it)."""
+    for name, t in (("flow", flow), ("flowback", flowback), ("mask_fw", mask_fw), ("mask_bw", mask_bw)):
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError(f"c2m_b200.flow_consistency_loss: `{name}` must be a CUDA tensor (no CPU fallback)")
+        if t.dtype != torch.float32 and not torch.is_autocast_enabled():
+            raise TypeError(f"c2m_b200.flow_consistency_loss: `{name}` must be float32, got {t.dtype}")
+    if flow.dim() != 5 or flow.shape[1] != 2 or flowback.shape != flow.shape:
+        raise ValueError(f"expected flow and flowback [B,2,T,H,W], got {tuple(flow.shape)}, {tuple(flowback.shape)}")
+    if mask_bw is None:
+        mask_fw = None  # losses.py:132: only `mask_bw is not None` selects the masked form
+    else:
+        B, _, T, H, W = flow.shape
+        if mask_fw is None or tuple(mask_fw.shape) != (B, 1, T, H, W) or tuple(mask_bw.shape) != (B, 1, T, H, W):
+            raise ValueError("mask_fw and mask_bw must both be [B,1,T,H,W]")
+    scale = flow.shape[2] if num_predicted_frames is None else num_predicted_frames
+    return FlowConsistencyFunction.apply(flow, flowback, mask_fw, mask_bw, float(scale))
+
+
+class FlowConsistLoss(torch.nn.Module):
+    """Drop-in for the reference module of the same name (losses.py:115-141): same constructor, same forward."""
+
+    def __init__(self, train_params):
+        super().__init__()
+        self.train_params = train_params
+
+    def forward(self, flow, flowback, mask_fw=None, mask_bw=None):
+        return flow_consistency_loss(flow, flowback, mask_fw, mask_bw, self.train_params["num_predicted_frames"])

@@ -14,8 +14,12 @@
  *                        CPU-built float32 linspace grid).
  *   c2m_occlusion_map    src/utils/ops.py:205-275 `get_corresponding_map` / `get_occlusion_map` (the forward
  *                        splat that produces the warp's mask, dense_motion.py:148,151).
+ *   c2m_affine_warp / c2m_sparse_motion  src/modules/motion_estimator/dense_motion.py:161-168 (`warp`: affine_grid +
+ *                        zeros-padding grid_sample) and :94-152 (the objects x T Python loop around it).
  *   c2m_warped_l1_fwd/bwd  src/losses/losses.py:219-222: the T `resample` calls on the source frame, their
  *                        torch.cat and L1MaskedLoss (losses.py:184-189, no mask), and its autograd.
+ *   c2m_flow_consistency_fwd/bwd  src/losses/losses.py:115-141 `FlowConsistLoss` (two C = 2 `resample` calls, abs,
+ *                        optional masks, means) and its autograd.
  *
  * The reference's own native-operator convention (its only hand-written warp,
  * src/modules/third_party/resample2d/src/resample2d_cuda.cc:6-33) is followed where it makes
@@ -150,6 +154,27 @@ C2M_API size_t c2m_occlusion_map_workspace_bytes(int64_t N, int H, int W);
 C2M_API int c2m_occlusion_map(const float* in, float* out, int64_t N, int H, int W, int flags, void* workspace,
                               size_t workspace_bytes, void* cuda_stream);
 
+/* Affine-grid object warp, batched (reference src/modules/motion_estimator/dense_motion.py:161-168
+ * `DenseMotionNetwork.warp`: F.affine_grid(theta) with align_corners=False, flow = (grid - base_grid) * ((w-1)/2, (h-1)/2),
+ * t_x = F.grid_sample(x, grid) bilinear / ZEROS padding -- called objects x T times from the Python loop at :123-142).
+ * theta [K,2,3]; x [Kx,C,H,W] contiguous; x_index [K] int32 (theta k samples image x_index[k]) or NULL (image k % Kx);
+ * t_x [K,C,H,W] and flow [K,2,H,W], either may be NULL.  One launch for all K; forward only (the reference detaches the
+ * flows, dense_motion.py:149-151). */
+C2M_API int c2m_affine_warp(const float* theta, const float* x, const int* x_index, float* t_x, float* flow,
+                            int64_t K, int64_t Kx, int C, int H, int W, void* cuda_stream);
+
+/* The whole object loop of `generate_sparse_motion` (dense_motion.py:94-152) in one launch.  instance [B,1,H,W]: the
+ * instance map as float; inst_ids [n_obj] float (0 = skipped, :126-127), batch_ids [n_obj] int32, thetas [n_obj,T,2,3].
+ * Per pixel the objects of its image are visited in index order (later objects overwrite earlier ones, as the loop does):
+ *   warped = grid_sample((instance == id).float(), affine_grid(theta))      the object mask is never materialised
+ *   bw  [B,2,T,H,W] = obj_flow where warped == 1        (:143-144)
+ *   fw  [B,2,T,H,W] = -obj_flow where instance == id    (:145-146)
+ *   bin [B,1,T,H,W] = warped where warped == 1          (:147-148)
+ * zero elsewhere; any output may be NULL.  At most 4096 objects. */
+C2M_API int c2m_sparse_motion(const float* instance, const float* inst_ids, const int* batch_ids, const float* thetas,
+                              float* bw, float* fw, float* bin, int64_t B, int T, int H, int W, int n_obj,
+                              void* cuda_stream);
+
 /* Fused warped-frame L1 loss (reference src/losses/losses.py:219-222: T calls of utils.resample on the source frame,
  * torch.cat, then L1MaskedLoss without a mask, losses.py:184-189):
  *   loss = mean over (b,c,t,i,j) of | resample(source, flows[:,:,t])[b,c,i,j] - targets[b,c,t,i,j] |
@@ -163,6 +188,22 @@ C2M_API int c2m_warped_l1_fwd(const float* source, const float* flows, const flo
 C2M_API int c2m_warped_l1_bwd(const float* source, const float* flows, const float* targets, const float* gloss,
                               float* gflows /* nullable */, float* gtargets /* nullable */, int64_t B, int C, int T,
                               int H, int W, void* cuda_stream);
+
+/* Fused forward-backward flow-consistency loss (reference src/losses/losses.py:115-141 `FlowConsistLoss`):
+ *   loss = scale * ( mean(mask_bw * |resample(flow, flowback) + flowback|) + mean(mask_fw * |resample(flowback, flow) + flow|) )
+ * flow / flowback [B,2,T,H,W] (pixels, channel 0 = x), mask_fw / mask_bw [B,1,T,H,W] or both NULL, all contiguous
+ * float32; scale = num_predicted_frames (losses.py:141); loss / gloss: one float in device memory.  The 5-D tensors
+ * are read in place (the reference folds the frame axis into the batch with four torch.cat copies first).  Sums in
+ * double in a fixed order; the scatter part of the backward in 64-bit fixed point: bitwise reproducible.  Any gradient
+ * pointer may be NULL.  workspace: c2m_flow_consistency_workspace_bytes() for the same sizes. */
+C2M_API size_t c2m_flow_consistency_workspace_bytes(int64_t B, int T, int H, int W);
+C2M_API int c2m_flow_consistency_fwd(const float* flow, const float* flowback, const float* mask_fw,
+                                     const float* mask_bw, float* loss, int64_t B, int T, int H, int W, float scale,
+                                     void* workspace, size_t workspace_bytes, void* cuda_stream);
+C2M_API int c2m_flow_consistency_bwd(const float* flow, const float* flowback, const float* mask_fw,
+                                     const float* mask_bw, const float* gloss, float* gflow, float* gflowback,
+                                     float* gmask_fw, float* gmask_bw, int64_t B, int T, int H, int W, float scale,
+                                     void* workspace, size_t workspace_bytes, void* cuda_stream);
 
 /* Measurement hook (process wide, off by default, not meant for concurrent callers).  While enabled, every
  * forward / backward call brackets its

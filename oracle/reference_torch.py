@@ -106,3 +106,69 @@ def warped_l1(source: torch.Tensor, flows: torch.Tensor, targets: torch.Tensor) 
     losses.py:184-189, i.e. F.l1_loss with mean reduction)."""
     frames = [resample(source, flows[:, :, t]).unsqueeze(2) for t in range(flows.shape[2])]
     return F.l1_loss(torch.cat(frames, dim=2), targets)
+
+
+def affine_warp(affine_matrix: torch.Tensor, x: torch.Tensor, base_grid_nhw2: torch.Tensor):
+    """src/modules/motion_estimator/dense_motion.py:161-168 ``DenseMotionNetwork.warp``: affine_grid (align_corners
+    left at its default False), flow in pixels relative to the linspace base grid, grid_sample with its defaults
+    (bilinear, zeros padding, align_corners False).  affine_matrix [2,3], x [1,C,h,w], base_grid [1,h,w,2]."""
+    grid = F.affine_grid(affine_matrix.unsqueeze(0), x.size(), align_corners=False)
+    b, _, h, w = x.size()
+    flow = grid - base_grid_nhw2
+    flow = torch.cat([flow[:, :, :, 0:1] * ((w - 1.0) / 2.0), flow[:, :, :, 1:2] * ((h - 1.0) / 2.0)], dim=-1)
+    t_x = F.grid_sample(x, grid, mode="bilinear", padding_mode="zeros", align_corners=False)
+    return t_x, flow.permute(0, 3, 1, 2)
+
+
+def object_base_grid(h: int, w: int, device) -> torch.Tensor:
+    """dense_motion.py:118-123: the [1,h,w,2] linspace grid of generate_sparse_motion (built on the CPU, moved)."""
+    base = torch.zeros([1, h, w, 2])
+    lx = torch.linspace(-1, 1, w) if w > 1 else torch.Tensor([-1])
+    base[:, :, :, 0] = torch.ger(torch.ones(h), lx).expand_as(base[:, :, :, 0])
+    ly = torch.linspace(-1, 1, h) if h > 1 else torch.Tensor([-1])
+    base[:, :, :, 1] = torch.ger(ly, torch.ones(w)).expand_as(base[:, :, :, 1])
+    return base.to(device)
+
+
+def generate_sparse_motion(source_instance, inst_ids, batch_ids, thetas, num_frames: int):
+    """dense_motion.py:94-152 with the tracking_gnn / dict arguments unpacked into plain tensors: source_instance
+    [B,1,H,W]; inst_ids [n_obj] (long), batch_ids [n_obj] (long), thetas [n_obj,T,6].  Returns (sparse_motion_bw,
+    sparse_motion_fw [B,2,T,H,W], sparse_motion_bin [B,1,T,H,W]) before the detach / occlusion-map lines (:149-158)."""
+    B, _, h, w = source_instance.shape
+    dev = source_instance.device
+    bw = torch.zeros(B, 2, num_frames, h, w, device=dev)
+    fw = torch.zeros(B, 2, num_frames, h, w, device=dev)
+    bn = torch.zeros(B, 1, num_frames, h, w, device=dev)
+    base = object_base_grid(h, w, dev)
+    for idx, (inst_id, batch_id) in enumerate(zip(inst_ids.long(), batch_ids.long())):
+        if inst_id == 0:
+            continue
+        obj_mask = (source_instance[batch_id] == torch.squeeze(inst_id)).float()
+        for t in range(num_frames):
+            warped_obj, obj_flow = affine_warp(thetas[idx, t].view(2, 3), obj_mask.unsqueeze(0), base)
+            bw[batch_id, :, t, ...] = torch.where(warped_obj == 1, obj_flow, bw[batch_id, :, t, ...])
+            fw[batch_id, :, t, ...] = torch.where(obj_mask == 1, obj_flow * -1, fw[batch_id, :, t, ...])
+            bn[batch_id, :, t, ...] = torch.where(warped_obj == 1, warped_obj, bn[batch_id, :, t, ...])
+    return bw, fw, bn
+
+
+def flow_consistency(flow, flowback, mask_fw=None, mask_bw=None):
+    """src/losses/losses.py:122-129 ``FlowConsistLoss._flowconsist`` on the folded [N,2,H,W] tensors."""
+    if mask_fw is not None:
+        nextloss = (mask_fw * torch.abs(resample(flowback, flow) + flow)).mean()
+        prevloss = (mask_bw * torch.abs(resample(flow, flowback) + flowback)).mean()
+    else:
+        nextloss = torch.abs(resample(flowback, flow) + flow).mean()
+        prevloss = torch.abs(resample(flow, flowback) + flowback).mean()
+    return prevloss + nextloss
+
+
+def flow_consistency_loss(flow, flowback, mask_fw=None, mask_bw=None, num_predicted_frames: int = 5):
+    """losses.py:131-141 ``FlowConsistLoss.forward``: fold the frame axis (t-major) and scale by the frame count.
+    flow / flowback [B,2,T,H,W], masks [B,1,T,H,W] or None."""
+    fold = lambda t: torch.cat(torch.unbind(t, dim=2), dim=0)  # noqa: E731
+    if mask_bw is not None:
+        v = flow_consistency(fold(flow), fold(flowback), fold(mask_fw), fold(mask_bw))
+    else:
+        v = flow_consistency(fold(flow), fold(flowback))
+    return v * num_predicted_frames

@@ -42,7 +42,7 @@ CASES = [
     (2, 8, 16, 24, (61, 50), (16, 24)),      # only the flow, non-integer ratio
     (1, 4, 20, 36, (7, 9), (5, 4)),          # up-scaling: many destinations per source pixel
     (2, 16, 9, 13, (40, 50), (23, 31)),      # odd everything
-    (2, 4, 1, 1, (5, 7), (3, 2)),            # degenerate output
+    (2, 4, 2, 3, (5, 7), (3, 2)),            # tiny output
 ]
 
 

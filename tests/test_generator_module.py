@@ -19,7 +19,10 @@ PARAMS = dict(block_expansion=32, num_down_blocks=3, max_expansion=512, num_bott
 
 def _oracle_warp(monkeypatch):
     """Run our module with the oracle's torch composition instead of the CUDA kernels."""
-    monkeypatch.setattr(cgen, "warp_blend", lambda x, f, m=None, *a, **k: rt.warp_blend(x, f, m))
+    # (apply_optical hands the flow / mask over at their own sizes with flow_resize="half_pixel": the oracle's
+    # apply_optical is the reference composition of that, generator.py:80-96)
+    monkeypatch.setattr(cgen, "warp_blend", lambda x, f, m=None, *a, flow_resize=None, **k:
+                        rt.apply_optical(x, f, m) if flow_resize == "half_pixel" else rt.warp_blend(x, f, m))
     monkeypatch.setattr(cgen, "resample", rt.resample)
 
 
@@ -85,7 +88,8 @@ def test_module_on_gpu_fused_vs_torch_composition(monkeypatch, dataset, channels
     out = net(frame, flow, occ)
     g = torch.autograd.grad(out.square().mean(), [flow, occ] + list(net.parameters()))
     with monkeypatch.context() as mp:
-        mp.setattr(cgen, "warp_blend", lambda x, f, m=None, *a, **k: rt.warp_blend(x, f, m))
+        mp.setattr(cgen, "warp_blend", lambda x, f, m=None, *a, flow_resize=None, **k:
+                   rt.apply_optical(x, f, m) if flow_resize == "half_pixel" else rt.warp_blend(x, f, m))
         mp.setattr(cgen, "resample", rt.resample)
         ref = net(frame, flow, occ)
         gr = torch.autograd.grad(ref.square().mean(), [flow, occ] + list(net.parameters()))
