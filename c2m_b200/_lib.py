@@ -11,7 +11,8 @@ import os
 import threading
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libc2m_warp.so")
+# C2M_WARP_LIB points at another build of the same library (kernel tuning: tools/build_variants.py)
+LIB_PATH = os.environ.get("C2M_WARP_LIB") or os.path.join(_PKG, "libc2m_warp.so")
 
 PAD_BORDER = 0
 PAD_ZEROS = 1

@@ -386,8 +386,10 @@ __device__ __forceinline__ void gx_issue(const char* gl, int cnt, const int4& e0
   const float4* a1 = key_ptr(gl, e0.z);
   const float4* a2 = key_ptr(gl, e1.x);
   const float4* a3 = key_ptr(gl, e1.z);
-  // entries past the count hold weight 0: their loads are predicated off (L1 bandwidth is what
-  // bounds this kernel), the arithmetic stays unconditional
+  // entries past the count: their loads are predicated off and read as zero.  (Leaving the registers undefined
+  // instead saves the clears but makes every destination register live across the whole loop -- a predicated load
+  // preserves its old value -- and the kernel spills; unpredicated loads of a dummy row cost L1 bandwidth.  Both
+  // measured slower, profiles/r2_gather_variants_ab.txt.)
 #pragma unroll
   for (int q = 0; q < NQ; ++q) {
     v[0][q] = ldg_batch_if(a0 + q * LP, cnt > 0);
@@ -402,16 +404,22 @@ __device__ __forceinline__ void gx_issue(const char* gl, int cnt, const int4& e0
 template <int LP, int NQ, int NP>
 __device__ __forceinline__ void gx_finish(const char* gl, char* po, int cnt, const int4& e0, const int4& e1,
                                           const int4* ent, int pstride, const float4 (&v)[4][NQ]) {
-  // slots past the count may hold anything (their loads were predicated off and read as zero): weight 0
-  const float w0 = cnt > 0 ? __int_as_float(e0.y) : 0.f, w1 = cnt > 1 ? __int_as_float(e0.w) : 0.f;
-  const float w2 = cnt > 2 ? __int_as_float(e1.y) : 0.f, w3 = cnt > 3 ? __int_as_float(e1.w) : 0.f;
+  // slots past the count contribute nothing (their loads were predicated off): the accumulation is predicated too
+  const float w[4] = {__int_as_float(e0.y), __int_as_float(e0.w), __int_as_float(e1.y), __int_as_float(e1.w)};
   float4 acc[NQ];
 #pragma unroll
-  for (int q = 0; q < NQ; ++q) {
-    acc[q].x = fmaf(w3, v[3][q].x, fmaf(w2, v[2][q].x, fmaf(w1, v[1][q].x, w0 * v[0][q].x)));
-    acc[q].y = fmaf(w3, v[3][q].y, fmaf(w2, v[2][q].y, fmaf(w1, v[1][q].y, w0 * v[0][q].y)));
-    acc[q].z = fmaf(w3, v[3][q].z, fmaf(w2, v[2][q].z, fmaf(w1, v[1][q].z, w0 * v[0][q].z)));
-    acc[q].w = fmaf(w3, v[3][q].w, fmaf(w2, v[2][q].w, fmaf(w1, v[1][q].w, w0 * v[0][q].w)));
+  for (int q = 0; q < NQ; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (cnt > k) {
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        acc[q].x = fmaf(w[k], v[k][q].x, acc[q].x);
+        acc[q].y = fmaf(w[k], v[k][q].y, acc[q].y);
+        acc[q].z = fmaf(w[k], v[k][q].z, acc[q].z);
+        acc[q].w = fmaf(w[k], v[k][q].w, acc[q].w);
+      }
+    }
   }
   if (cnt > 4) {  // long list: two entries at a time
 #pragma unroll
@@ -542,6 +550,22 @@ __device__ __forceinline__ void dot_finish(const DotRegs<NQ>& r, float& sa, floa
   }
 }
 
+// Sum four per-lane partial values over the LP lanes of a pixel with 2 + 1 + log2(LP/4) shuffles instead of
+// 4 * log2(LP): after the first exchange a lane carries two of the sums, after the second one.  On return the lanes
+// with lq % (LP/4) == 0 hold the complete sum number lq / (LP/4) (0: sa, 1: sb, 2: sc, 3: se).
+template <int LP>
+__device__ __forceinline__ float reduce4(float sa, float sb, float sc, float se, int lq) {
+  static_assert(LP >= 4, "four sums need at least four lanes");
+  const bool hi = (lq & (LP / 2)) != 0;
+  float r0 = (hi ? sc : sa) + __shfl_xor_sync(0xffffffffu, hi ? sa : sc, LP / 2);
+  float r1 = (hi ? se : sb) + __shfl_xor_sync(0xffffffffu, hi ? sb : se, LP / 2);
+  const bool hi2 = (lq & (LP / 4)) != 0;
+  float r = (hi2 ? r1 : r0) + __shfl_xor_sync(0xffffffffu, hi2 ? r0 : r1, LP / 4);
+#pragma unroll
+  for (int o = LP / 8; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+  return r;
+}
+
 //   LP  lanes per pixel (a warp moves 32/LP pixels side by side)
 //   QI  float4 groups per lane when C/4 == LP*QI exactly, 0 = run-time channel loop
 // The contributor lists are built by the CTA itself in shared memory from the row segments that segbin_kernel
@@ -562,6 +586,7 @@ __global__ void __launch_bounds__(256, 4) gather_nhwc_kernel(const __grid_consta
   // ax, ay, mask, flags (bits 0-3: corner inside the image, 4 / 5: x / y coordinate clipped -> zero
   // grad-flow); later the pixel's (gflow_x, gflow_y, gmask)
   __shared__ float4 s_aux[DO_GF ? TH : 1][TW];
+  __shared__ float4 s_sum[DO_GF ? TH : 1][TW];  // the pixel's four dot products sum_c gout[c] * x_corner[c]
   __shared__ int s_cnt[DO_GX ? TH : 1][TW];
   __shared__ int4 s_ent[DO_GX ? NP : 1][DO_GX ? TH : 1][TW];
   const Dims& d = p.d;
@@ -739,7 +764,6 @@ __global__ void __launch_bounds__(256, 4) gather_nhwc_kernel(const __grid_consta
     constexpr int NQ = QI > 0 ? QI : 1;
     float sa = 0.f, sb = 0.f, sc = 0.f, se = 0.f;  // sum_c gout[c] * x_corner[c]
     if (QI > 0) {
-      // both roles' loads go out before the first use: one exposed memory latency per step, not two
       int cnt = 0;
       int4 e0 = make_int4(0, 0, 0, 0), e1 = e0;
       float4 v[4][NQ];
@@ -792,32 +816,10 @@ __global__ void __launch_bounds__(256, 4) gather_nhwc_kernel(const __grid_consta
       }
     }
     if (DO_GF) {
-      const int pr = act ? pa : 0;
-      const float4 aux = s_aux[warp][pr];  // ax, ay, mask, flags
-      const int ok = __float_as_int(aux.w);
-      if (!(ok & 1)) sa = 0.f;  // corners outside the image contribute nothing (ATen within_bounds)
-      if (!(ok & 2)) sb = 0.f;
-      if (!(ok & 4)) sc = 0.f;
-      if (!(ok & 8)) se = 0.f;
-      // bilinear weights from the fractions: x1 - ix == 1 - ax and ix - x0 == ax, the expressions of make_geo
-      const float bxw = 1.f - aux.x, byw = 1.f - aux.y;
-      float gix = (sb - sa) * byw + (se - sc) * aux.y;
-      float giy = (sc - sa) * bxw + (se - sb) * aux.x;
-      float gm = fmaf(se, aux.x * aux.y, fmaf(sc, bxw * aux.y, fmaf(sb, aux.x * byw, sa * (bxw * byw))));
-#pragma unroll
-      for (int o = LP >> 1; o > 0; o >>= 1) {
-        gix += __shfl_xor_sync(0xffffffffu, gix, o);
-        giy += __shfl_xor_sync(0xffffffffu, giy, o);
-        gm += __shfl_xor_sync(0xffffffffu, gm, o);
-      }
-      // (the shuffles above are the convergence point between the group's reads of slot `pa` and this write)
-      if (lq == 0 && act) {
-        const float mm = HAS_MASK ? aux.z : 1.f;  // the sums used gout, not gout*mask
-        // d(clipped coordinate)/d(flow), as make_geo forms it: clip-grad * size/2 * 1/((size-1)/2)
-        const float gmx = ((ok & 16) ? 0.f : 1.f) * (0.5f * (float)d.W) * d.inv_bw;
-        const float gmy = ((ok & 32) ? 0.f : 1.f) * (0.5f * (float)d.H) * d.inv_bh;
-        s_aux[warp][pa] = make_float4(gix * mm * gmx, giy * mm * gmy, gm, 0.f);
-      }
+      // the four dot products of the pixel, summed over its LP lanes; the per-pixel algebra that turns them into
+      // grad-flow / grad-mask runs once per row below (lane = pixel), not once per step on every lane
+      const float r = reduce4<LP>(sa, sb, sc, se, lq);
+      if (act && (lq % (LP / 4)) == 0) reinterpret_cast<float*>(&s_sum[warp][pa])[lq / (LP / 4)] = r;
     }
     if (DO_GX) gxl += G * pxb;
     gol += G * pxb;
@@ -825,7 +827,21 @@ __global__ void __launch_bounds__(256, 4) gather_nhwc_kernel(const __grid_consta
   if (DO_GF) {
     __syncwarp();
     if (live) {
-      const float4 res = s_aux[warp][lane];
+      const float4 sum = s_sum[warp][lane];
+      const float4 aux = s_aux[warp][lane];  // ax, ay, mask, flags
+      const int ok = __float_as_int(aux.w);
+      // corners outside the image contribute nothing (ATen within_bounds)
+      const float qa = (ok & 1) ? sum.x : 0.f, qb = (ok & 2) ? sum.y : 0.f;
+      const float qc = (ok & 4) ? sum.z : 0.f, qe = (ok & 8) ? sum.w : 0.f;
+      // bilinear weights from the fractions: x1 - ix == 1 - ax and ix - x0 == ax, the expressions of make_geo
+      const float bxw = 1.f - aux.x, byw = 1.f - aux.y;
+      const float gix = (qb - qa) * byw + (qe - qc) * aux.y;
+      const float giy = (qc - qa) * bxw + (qe - qb) * aux.x;
+      const float gm = fmaf(qe, aux.x * aux.y, fmaf(qc, bxw * aux.y, fmaf(qb, aux.x * byw, qa * (bxw * byw))));
+      const float mm = HAS_MASK ? aux.z : 1.f;  // the sums used gout, not gout*mask
+      // d(clipped coordinate)/d(flow), as make_geo forms it: clip-grad * size/2 * 1/((size-1)/2)
+      const float gmx = ((ok & 16) ? 0.f : 1.f) * (0.5f * (float)d.W) * d.inv_bw;
+      const float gmy = ((ok & 32) ? 0.f : 1.f) * (0.5f * (float)d.H) * d.inv_bh;
       float* gfp = p.gflow;
       float* gmp = p.gmask;
       if (gridDim.y > 1) {
@@ -834,13 +850,14 @@ __global__ void __launch_bounds__(256, 4) gather_nhwc_kernel(const __grid_consta
       }
       if (gfp) {
         float* gf = gfp + (int64_t)n * 2 * HW + pix;
-        gf[0] = res.x;
-        gf[HW] = res.y;
+        gf[0] = gix * mm * gmx;
+        gf[HW] = giy * mm * gmy;
       }
-      if (gmp) gmp[(int64_t)n * HW + pix] = res.z;
+      if (gmp) gmp[(int64_t)n * HW + pix] = gm;
     }
   }
 }
+
 
 // ---------------------------------------------------------------------------------------------
 // NCHW gather: one thread per pixel, channel loop.

@@ -95,6 +95,20 @@ def patch_reference(verbose: bool = False):
         cls.deform_input = staticmethod(deform_input)
         cls.apply_optical = apply_optical
         done.append(("modules.generator.generator", "OcclusionAwareGenerator.{deform_input,apply_optical}"))
+    # the affine-grid object warp and its objects x T loop (dense_motion.py:94-168)
+    dm_mod = sys.modules.get("modules.motion_estimator.dense_motion")
+    if dm_mod is not None and hasattr(dm_mod, "DenseMotionNetwork"):
+        from . import motion
+        cls = dm_mod.DenseMotionNetwork
+        cls.warp = staticmethod(motion.affine_warp)
+        cls.generate_sparse_motion = motion.generate_sparse_motion
+        done.append(("modules.motion_estimator.dense_motion", "DenseMotionNetwork.{warp,generate_sparse_motion}"))
+    # the flow-consistency loss (losses.py:115-141): same constructor, fused forward
+    loss_mod = sys.modules.get("losses.losses")
+    if loss_mod is not None and hasattr(loss_mod, "FlowConsistLoss"):
+        from . import loss
+        loss_mod.FlowConsistLoss.forward = loss.FlowConsistLoss.forward
+        done.append(("losses.losses", "FlowConsistLoss.forward"))
     if verbose:
         for d in done:
             print("c2m_b200: patched %s.%s" % d)

@@ -1,0 +1,17 @@
+# Development tool: time the channels-last gather for each library variant under c2m_b200/variants (tools/build_variants.py)
+# and check parity with it.  Output: gpurun_out/${TAG}_ab.txt
+T=${TAG:-ab}
+OUT=gpurun_out/${T}_ab.txt
+: > $OUT
+B="python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-traffic --e2e-steps 0 --torch-cuda-steps 0 --no-pyramids --no-configs --no-other-layout"
+for lib in "" $(ls c2m_b200/variants/*.so 2>/dev/null); do
+  for st in 1 0; do
+    name=${lib:-default}
+    C2M_WARP_LIB=${lib:+$PWD/$lib} C2M_WARP_GATHER_STAGED=$st $B 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); r=d['roofline']
+print('%-36s staged=$st  step %.4f ms  fwd %.4f  bwd %.4f  gather %.4f  (frac %.3f, step frac %.3f)' % ('$name', d['ms_per_step'], r['fwd']['ms'], r['bwd']['ms'], r['kernels_alone']['bwd_gather_ms'], r['frac'], r['fwd_bwd']['frac']))" >> $OUT
+    C2M_WARP_LIB=${lib:+$PWD/$lib} C2M_WARP_GATHER_STAGED=$st python -m pytest tests/test_gpu_parity.py -q -x -k "channels_last or full_size or sliced or deterministic" 2>&1 | tail -1 >> $OUT
+  done
+done
+cat $OUT
