@@ -94,6 +94,18 @@ struct BwdParams {
   int64_t ovf_stride;       // channel-sliced gather: slice s flags its own list overflows in ovf[(s + 1) * ovf_stride + pixel]
                             // and lists them as pixel | (s + 1) << 24 (tag 0: all channels, from segbin_kernel)
   float* gpart;             // channel-sliced gather (small levels): [slices][gflow N*2*HW | gmask N*HW] partial sums
+  // incoherent flows (a row segment whose samples spread over more than 12 destination tiles): its pixels are
+  // registered one by one with the destination tiles they touch (counting sort keyed by tile: count in segbin_kernel,
+  // flex_scan_kernel, flex_fill_kernel) and those tiles' grad-input is formed by gather_flex_kernel
+  int* bcount;              // [x_batch * tiles] pixel registrations per destination tile (0: the tile is not "flex")
+  int* bstart;              // [x_batch * tiles] start of the tile's registrations in `pool`
+  int* bfill;               // [x_batch * tiles] fill cursor
+  int* pool;                // [4 * N*H*W] registered output pixels, grouped by destination tile
+  int* iseg_count;          // number of incoherent segments ...
+  int* iseg_list;           // ... and their ids (frame * segments per frame + segment)
+  int* flex_count;          // number of flex tiles, their ids, and the work-queue cursor of gather_flex_kernel
+  int* flex_list;
+  int* flex_next;
 };
 
 // One output sample of ATen's upsample_bilinear2d: plane `pl` [Hs, Ws] sampled for output pixel (i, j).
@@ -252,6 +264,12 @@ __device__ __forceinline__ float fixed_scale_from(float mx, int count_log2) {
   return exp2f((float)k);
 }
 __device__ __forceinline__ long long to_fixed(float term, float scale) { return __float2ll_rn(term * scale); }
+// 1 / scale for the one conversion back to float -- or NaN when the upstream gradient holds a non-finite value (the
+// max-reductions report it as +inf): an integer sum cannot carry NaN / inf, so the destinations summed that way are
+// poisoned as a whole instead of coming back finite (ATen and the float paths propagate non-finite terms).
+__device__ __forceinline__ float fixed_inv_scale(float mx, float scale) {
+  return (mx < 3.0e38f) ? 1.f / scale : __int_as_float(0x7fc00000);
+}
 
 // ---------------------------------------------------------------------------------------------
 // mbarrier + TMA (cp.async.bulk.tensor) wrappers

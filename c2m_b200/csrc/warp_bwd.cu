@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(256) absmax_kernel(const BwdParams p, unsigned
     const int64_t gb = (int64_t)n * p.gs[0] + i * p.gs[2] + j * p.gs[3];
     for (int c = 0; c < d.C; ++c) {
       const float v = fabsf(p.gout[gb + c * p.gs[1]]) * m;
-      mx = (v == v) ? fmaxf(mx, v) : mx;
+      mx = (v == v) ? fmaxf(mx, v) : __int_as_float(0x7f800000);  // NaN counts as +inf: "non-finite seen"
     }
   }
   for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -117,7 +117,8 @@ __global__ void __launch_bounds__(256) absmax_kernel(const BwdParams p, unsigned
 }
 
 __global__ void __launch_bounds__(256) fix2float_kernel(const long long* acc, float* gx, int64_t n, BwdParams p) {
-  const double inv = 1.0 / (double)fixed_scale(p);
+  // (NaN when the upstream gradient held a non-finite value: an integer sum cannot carry it)
+  const double inv = (double)fixed_inv_scale(__uint_as_float(*p.maxbits), fixed_scale(p));
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x)
     gx[idx] = (float)((double)acc[idx] * inv);
 }

@@ -110,6 +110,34 @@ __global__ void __launch_bounds__(256) bin_kernel(const BwdParams p) {
 // tile later recomputes the geometry of its candidates and builds the per-pixel lists in shared memory.
 // A segment whose box spans too many tiles (incoherent flow), or whose registration does not fit a tile's
 // candidate array, hands the affected contributions to overflow_kernel instead (flag byte + compact list).
+__device__ __forceinline__ const float4* key_ptr(const char* base, int key) {
+  return reinterpret_cast<const float4*>(base + ((int64_t)(uint32_t)key << 4));  // keys count 16-byte units
+}
+
+// The destination tiles (8 x 32, numbered inside one image) that a pixel's in-image, non-zero-weight corners fall in:
+// at most four, without repeats.  Evaluated from the pixel RECORD (unclamped nw corner, fractions, mask) with the
+// weight expressions of the local binning, so that the count pass (segbin_kernel), the fill pass (flex_fill_kernel)
+// and the gather (gather_flex_kernel) agree exactly on what a pixel contributes where.
+__device__ __forceinline__ int rec_tiles(const Dims& d, int ux0, int uy0, float ax, float ay, float sm, int tiles_x,
+                                         int (&tl)[4]) {
+  const float bxw = 1.f - ax, byw = 1.f - ay;
+  const float ws[4] = {(bxw * byw) * sm, (ax * byw) * sm, (bxw * ay) * sm, (ax * ay) * sm};
+  int nt = 0;
+  tl[0] = tl[1] = tl[2] = tl[3] = -1;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int gx = ux0 + (k & 1), gy = uy0 + (k >> 1);
+    if ((unsigned)gx < (unsigned)d.W && (unsigned)gy < (unsigned)d.H && ws[k] != 0.f) {
+      const int t = (gy >> 3) * tiles_x + (gx >> 5);
+      bool seen = false;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) seen |= (q < nt) && (tl[q] == t);
+      if (!seen) tl[nt++] = t;
+    }
+  }
+  return nt;
+}
+
 __global__ void __launch_bounds__(256) segbin_kernel(const BwdParams p) {
   constexpr int TH = 8, TW = 32, kMaxCells = 12;
   const Dims& d = p.d;
@@ -127,6 +155,8 @@ __global__ void __launch_bounds__(256) segbin_kernel(const BwdParams p) {
   bool act[4] = {false, false, false, false};
   unsigned inimg = 0;  // corners inside the image
   const int idx = n * HW + i * d.W + j;
+  int r_ux0 = -100, r_uy0 = -100;  // the pixel record, kept for the incoherent route
+  float r_ax = 0.f, r_ay = 0.f, r_m = 0.f;
   // deterministic mode, called once on every way out: per destination an upper bound of the contributions its
   // list will see (all in-image corners, whatever their weight), or bit 30 for a contribution that goes to
   // overflow_kernel instead; zero_hot_rows_kernel clears the accumulator rows of the destinations that can
@@ -159,6 +189,7 @@ __global__ void __launch_bounds__(256) segbin_kernel(const BwdParams p) {
     const int uy0 = g.oknw | g.okne ? g.y0 : (g.oksw | g.okse ? g.y1 - 1 : -100);
     p.pixrec[idx] = make_int4((ux0 & 0xffff) | (uy0 << 16), __float_as_int(g.ax), __float_as_int(g.ay),
                               __float_as_int(m));
+    r_ux0 = ux0; r_uy0 = uy0; r_ax = g.ax; r_ay = g.ay; r_m = m;
     act[0] = g.oknw && g.wnw * m != 0.f;
     act[1] = g.okne && g.wne * m != 0.f;
     act[2] = g.oksw && g.wsw * m != 0.f;
@@ -183,6 +214,23 @@ __global__ void __launch_bounds__(256) segbin_kernel(const BwdParams p) {
   const int ncols = xmax / TW - tx0 + 1, nrows = ymax / TH - ty0 + 1;
   const int ncell = ncols * nrows;
   unsigned fail;
+  if (ncell > kMaxCells && p.bcount) {
+    // incoherent flow: the segment's pixels register one by one with the destination tiles they touch (count pass of
+    // a counting sort keyed by tile; flex_scan_kernel / flex_fill_kernel complete it, gather_flex_kernel forms those
+    // tiles' grad-input) -- no per-contribution atomics on grad-input, in deterministic mode none on the accumulator
+    int tl[4] = {-1, -1, -1, -1};
+    if (live) rec_tiles(d, r_ux0, r_uy0, r_ax, r_ay, r_m, tiles_x, tl);
+    int* bc = p.bcount + (n % d.x_batch) * tiles_y * tiles_x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      // clamped out-of-bounds flows send most of a segment to the same border tile: one atomic per distinct tile
+      const unsigned peers = __match_any_sync(0xffffffffu, tl[k]);
+      if (tl[k] >= 0 && lane == __ffs(peers) - 1) atomicAdd(bc + tl[k], __popc(peers));
+    }
+    if (lane == 0) p.iseg_list[atomicAdd(p.iseg_count, 1)] = n * (d.H * tiles_x) + rs;
+    tally(0u);
+    return;
+  }
   if (ncell > kMaxCells) {
     fail = 0xffffffffu;
     if (p.cnt) {
@@ -366,6 +414,330 @@ __global__ void __launch_bounds__(256) overflow_kernel(const BwdParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------
+constexpr int kFlexHeavy = 768;            // a tile with more registered pixels than this is "heavy": gather_flex_kernel
+constexpr int kFlexLong = 64;              // a destination list longer than this is summed by all warps of the CTA
+constexpr int kFlexChunk = 768;            // candidate pixels per chunk
+constexpr int kFlexCap = 4 * kFlexChunk;   // contributions per chunk (four corners each), + padding to even starts
+
+// Incoherent flows: the counting sort's middle passes.
+// flex_scan_kernel (one block): exclusive scan of the per-tile registration counts -> start offsets into the pool, and
+// the compact list of the heavy tiles (count > kFlexHeavy), in tile order.  Exits at once when no segment was incoherent.
+__global__ void __launch_bounds__(1024) flex_scan_kernel(const BwdParams p, int ntile) {
+  __shared__ int s_a[32], s_b[32];
+  if (*reinterpret_cast<const volatile int*>(p.iseg_count) == 0) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int per = (ntile + 1023) / 1024;
+  const int t0 = min(tid * per, ntile), t1 = min(t0 + per, ntile);
+  int sum = 0, nz = 0;
+  for (int t = t0; t < t1; ++t) {
+    const int c = p.bcount[t];
+    sum += c;
+    nz += c > kFlexHeavy;
+  }
+  int isum = sum, inz = nz;  // inclusive scans over the block
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int a = __shfl_up_sync(0xffffffffu, isum, o), b = __shfl_up_sync(0xffffffffu, inz, o);
+    if (lane >= o) { isum += a; inz += b; }
+  }
+  if (lane == 31) { s_a[warp] = isum; s_b[warp] = inz; }
+  __syncthreads();
+  if (warp == 0) {
+    int a = s_a[lane], b = s_b[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int ua = __shfl_up_sync(0xffffffffu, a, o), ub = __shfl_up_sync(0xffffffffu, b, o);
+      if (lane >= o) { a += ua; b += ub; }
+    }
+    s_a[lane] = a;
+    s_b[lane] = b;
+  }
+  __syncthreads();
+  int start = isum - sum + (warp ? s_a[warp - 1] : 0), fpos = inz - nz + (warp ? s_b[warp - 1] : 0);
+  for (int t = t0; t < t1; ++t) {
+    const int c = p.bcount[t];
+    p.bstart[t] = start;
+    start += c;
+    if (c > kFlexHeavy) p.flex_list[fpos++] = t;
+  }
+  if (tid == 1023) *p.flex_count = fpos;
+}
+
+// flex_fill_kernel: one warp per incoherent segment writes its pixels into the pool ranges of the tiles they touch.
+__global__ void __launch_bounds__(256) flex_fill_kernel(const BwdParams p) {
+  constexpr int TH = 8, TW = 32;
+  const Dims& d = p.d;
+  const int nseg = *reinterpret_cast<const volatile int*>(p.iseg_count);
+  const int HW = d.H * d.W;
+  const int tiles_x = (d.W + TW - 1) / TW, tiles_y = (d.H + TH - 1) / TH;
+  const int segs = d.H * tiles_x;
+  const int lane = threadIdx.x & 31;
+  for (int k = blockIdx.x * 8 + (threadIdx.x >> 5); k < nseg; k += gridDim.x * 8) {
+    const int id = __ldg(p.iseg_list + k);
+    const int n = id / segs, rs = id - n * segs;
+    const int i = rs / tiles_x, bx = rs - i * tiles_x;
+    const int j = bx * TW + lane;
+    const int sidx = n * HW + i * d.W + j;
+    int tl[4] = {-1, -1, -1, -1};
+    if (j < d.W) {
+      const int4 rec = __ldg(p.pixrec + sidx);
+      rec_tiles(d, (int)(short)(rec.x & 0xffff), rec.x >> 16, __int_as_float(rec.y), __int_as_float(rec.z),
+                __int_as_float(rec.w), tiles_x, tl);
+    }
+    const int tb = (n % d.x_batch) * tiles_y * tiles_x;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const unsigned peers = __match_any_sync(0xffffffffu, tl[q]);
+      const int leader = __ffs(peers) - 1;
+      int base = 0;
+      if (tl[q] >= 0 && lane == leader) base = atomicAdd(p.bfill + tb + tl[q], __popc(peers));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (tl[q] >= 0) {
+        const int t = tb + tl[q];
+        const int pos = base + __popc(peers & ((1u << lane) - 1u));
+        if (pos < __ldg(p.bcount + t)) p.pool[__ldg(p.bstart + t) + pos] = sidx;
+      }
+    }
+  }
+}
+
+// gather_flex_kernel: grad-input of the flex tiles.  Persistent CTAs take tiles from a work queue.  A tile's
+// contributors are the pixels of its candidate segments (coherent neighbours) followed by its pool range; they are
+// processed in chunks of kFlexChunk pixels: count per destination pixel (shared-memory atomics), scan, fill -- a
+// counting sort by destination inside the tile, lists of any length -- then every destination pixel sums its list
+// with LP lanes across the channels (destinations dealt round robin over all lane groups of the CTA: clamped
+// out-of-bounds flows pile thousands of contributions on one border row).  Later chunks add to the first one's result.
+// DET: order-independent 64-bit fixed-point sums (the pool order is not reproducible).
+
+template <int LP, bool DET>
+__global__ void __launch_bounds__(256, 4) gather_flex_kernel(const BwdParams p) {
+  constexpr int TH = 8, TW = 32, NPIX = TH * TW;
+  __shared__ int s_cnt[NPIX], s_start[NPIX], s_fill[NPIX];
+  __shared__ alignas(16) int2 s_e[kFlexCap + NPIX + 4];
+  __shared__ int s_tile, s_wsum[8];
+  __shared__ union {  // pass 1 of the reduce: per-warp partial sums of one float4 group per lane
+    float4 f[8][LP];
+    long long i[8][LP][4];
+  } s_part;
+  const Dims& d = p.d;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tiles_x = (d.W + TW - 1) / TW, tiles_y = (d.H + TH - 1) / TH;
+  const int HW = d.H * d.W, C4 = d.C >> 2;
+  const int nflex = *reinterpret_cast<const volatile int*>(p.flex_count);
+  const int lq = lane % LP;
+  const float scale = DET ? fixed_scale_from(__uint_as_float(p.maxbits[0]) * __uint_as_float(p.maxbits[1]), p.count_log2) : 1.f;
+  const float inv_scale = DET ? fixed_inv_scale(__uint_as_float(p.maxbits[0]) * __uint_as_float(p.maxbits[1]), scale) : 1.f;
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_tile = atomicAdd(p.flex_next, 1);
+    __syncthreads();
+    const int item = s_tile;
+    if (item >= nflex) break;
+    const int T = __ldg(p.flex_list + item);
+    const int bx = T % tiles_x, r = T / tiles_x, by = r % tiles_y, n = r / tiles_y;  // n: image of x
+    const int ncand = min(__ldg(p.tcnt + T), p.cand_cap);
+    const int nb = __ldg(p.bcount + T), bs = __ldg(p.bstart + T);
+    const int2* tl = p.tlist + (int64_t)T * p.cand_cap;
+    const int V = ncand * 32 + nb;  // virtual candidate pixels: the segments' 32 lanes each, then the pool range
+    for (int v0 = 0; v0 < V; v0 += kFlexChunk) {
+      const bool first = v0 == 0, last = v0 + kFlexChunk >= V;
+      s_cnt[tid] = 0;
+      s_fill[tid] = 0;
+      __syncthreads();
+      // ---- pass 1: resolve this thread's candidate pixels, count their contributions per destination
+      int sidx[3];
+      int4 rec[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int v = v0 + k * 256 + tid;
+        sidx[k] = -1;
+        if (v < V) {
+          if (v < ncand * 32) {
+            const int2 seg = __ldg(tl + (v >> 5));
+            if ((v & 31) < seg.y) sidx[k] = seg.x + (v & 31);
+          } else {
+            sidx[k] = __ldg(p.pool + bs + (v - ncand * 32));
+          }
+        }
+        if (sidx[k] >= 0) {
+          rec[k] = __ldg(p.pixrec + sidx[k]);
+          const int ux0 = (int)(short)(rec[k].x & 0xffff), uy0 = rec[k].x >> 16;
+          const int dy = uy0 - by * TH, dx = ux0 - bx * TW;
+          if (dy >= -1 && dy < TH && dx >= -1 && dx < TW) {
+            const float ax = __int_as_float(rec[k].y), ay = __int_as_float(rec[k].z), sm = __int_as_float(rec[k].w);
+            const float bxw = 1.f - ax, byw = 1.f - ay;
+            const float ws[4] = {(bxw * byw) * sm, (ax * byw) * sm, (bxw * ay) * sm, (ax * ay) * sm};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const int cy = dy + (c >> 1), cx = dx + (c & 1);
+              if ((unsigned)cy < (unsigned)TH && (unsigned)cx < (unsigned)TW && uy0 + (c >> 1) < d.H &&
+                  ux0 + (c & 1) < d.W && ws[c] != 0.f)
+                atomicAdd(&s_cnt[cy * TW + cx], 1);
+            }
+          } else {
+            sidx[k] = -1;
+          }
+        }
+      }
+      __syncthreads();
+      // ---- exclusive scan of the counts, each rounded up to even (list starts stay 16-byte aligned)
+      {
+        const int c = (s_cnt[tid] + 1) & ~1;
+        int inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int u = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += u;
+        }
+        if (lane == 31) s_wsum[warp] = inc;
+        __syncthreads();
+        int base = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) base += (w < warp) ? s_wsum[w] : 0;
+        s_start[tid] = base + inc - c;
+      }
+      __syncthreads();
+      // ---- pass 2: fill the lists
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        if (sidx[k] < 0) continue;
+        const int ux0 = (int)(short)(rec[k].x & 0xffff), uy0 = rec[k].x >> 16;
+        const int dy = uy0 - by * TH, dx = ux0 - bx * TW;
+        const float ax = __int_as_float(rec[k].y), ay = __int_as_float(rec[k].z), sm = __int_as_float(rec[k].w);
+        const float bxw = 1.f - ax, byw = 1.f - ay;
+        const float ws[4] = {(bxw * byw) * sm, (ax * byw) * sm, (bxw * ay) * sm, (ax * ay) * sm};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int cy = dy + (c >> 1), cx = dx + (c & 1);
+          if ((unsigned)cy < (unsigned)TH && (unsigned)cx < (unsigned)TW && uy0 + (c >> 1) < d.H &&
+              ux0 + (c & 1) < d.W && ws[c] != 0.f) {
+            const int dp = cy * TW + cx;
+            s_e[s_start[dp] + atomicAdd(&s_fill[dp], 1)] = make_int2((int)((uint32_t)sidx[k] * (uint32_t)C4),
+                                                                    __float_as_int(ws[c]));
+          }
+        }
+      }
+      __syncthreads();
+      // ---- reduce: one WARP per destination pixel (the lists are long here): LP lanes across the float4 groups of a
+      // row, 32 / LP list entries side by side, four rounds of loads in flight per lane; the side-by-side partial
+      // sums meet through shuffles.  (Float: the pool order is not reproducible, neither is this sum -- like the
+      // atomics it replaces.  DET: 64-bit fixed point, any order gives the same bits.)
+      const char* gl = reinterpret_cast<const char*>(p.gout);
+      constexpr int P = 32 / LP;  // entries in flight side by side
+      const int sub = lane / LP;
+      // a destination with a very long list (the image corners collect thousands of clamped samples) is summed by
+      // ALL eight warps, each taking every eighth group of entries; the partial sums meet in shared memory.  Pass 0:
+      // the ordinary destinations, one per warp; pass 1: the long ones, one at a time, all warps together.
+      for (int pass = 0; pass < 2; ++pass)
+      for (int dp = pass ? 0 : warp; dp < NPIX; dp += pass ? 1 : 8) {
+        const int i = by * TH + dp / TW, j = bx * TW + dp % TW;
+        if (i >= d.H || j >= d.W) continue;
+        const int cnt = s_cnt[dp];
+        const bool longlist = cnt > kFlexLong;
+        if (longlist != (pass == 1)) continue;
+        if (cnt == 0 && !first && !(DET && last)) continue;  // nothing to add in this chunk (DET: the last one converts)
+        const int2* e = s_e + s_start[dp];
+        const int64_t D = (int64_t)n * HW + (int64_t)i * d.W + j;
+        const bool fold = DET && first && __ldcg(p.touched + D) != 0;  // terms pushed by overflow_kernel<DET>
+        const int kstep = pass ? 8 * 4 * P : 4 * P, koff = pass ? warp * 4 * P : 0;
+        for (int q0 = 0; q0 < C4; q0 += LP) {  // (warp-uniform trip count: the shuffles below need every lane)
+          const int q = q0 + lq;
+          const bool qv = q < C4;
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          long long ia[4] = {0, 0, 0, 0};
+          for (int k = koff + sub; k < cnt; k += kstep) {
+            int2 en[4];
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const bool on = qv && k + u * P < cnt;
+              en[u] = on ? e[k + u * P] : make_int2(0, 0);
+              v[u] = ldg_batch_if(key_ptr(gl, en[u].x) + q, on);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float w = __int_as_float(en[u].y);  // 0 when the slot is past the list
+              if (DET) {
+                ia[0] += to_fixed(w * v[u].x, scale);
+                ia[1] += to_fixed(w * v[u].y, scale);
+                ia[2] += to_fixed(w * v[u].z, scale);
+                ia[3] += to_fixed(w * v[u].w, scale);
+              } else {
+                acc.x = fmaf(w, v[u].x, acc.x);
+                acc.y = fmaf(w, v[u].y, acc.y);
+                acc.z = fmaf(w, v[u].z, acc.z);
+                acc.w = fmaf(w, v[u].w, acc.w);
+              }
+            }
+          }
+#pragma unroll
+          for (int o = LP; o < 32; o <<= 1) {  // the P side-by-side partial sums
+            if (DET) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c) ia[c] += __shfl_xor_sync(0xffffffffu, ia[c], o);
+            } else {
+              acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+              acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+              acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
+              acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+            }
+          }
+          if (pass) {  // the eight warps' partial sums, added in warp order by warp 0
+            __syncthreads();
+            if (sub == 0 && qv) {
+              if (DET) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) s_part.i[warp][lq][c] = ia[c];
+              } else {
+                s_part.f[warp][lq] = acc;
+              }
+            }
+            __syncthreads();
+            if (warp != 0) continue;
+            if (sub == 0 && qv) {
+#pragma unroll
+              for (int w = 1; w < 8; ++w) {
+                if (DET) {
+#pragma unroll
+                  for (int c = 0; c < 4; ++c) ia[c] += s_part.i[w][lq][c];
+                } else {
+                  const float4 o = s_part.f[w][lq];
+                  acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+                }
+              }
+            }
+          }
+          if (sub != 0 || !qv) continue;
+          float4* gxp = reinterpret_cast<float4*>(p.gx) + D * C4 + q;
+          if (DET) {
+            long long* ap = p.acc64 + D * d.C + q * 4;
+            if (!first || fold) {
+              const longlong2 h0 = __ldcg(reinterpret_cast<const longlong2*>(ap));
+              const longlong2 h1 = __ldcg(reinterpret_cast<const longlong2*>(ap + 2));
+              ia[0] += h0.x; ia[1] += h0.y; ia[2] += h1.x; ia[3] += h1.y;
+            }
+            if (last) {
+              *gxp = make_float4(__ll2float_rn(ia[0]) * inv_scale, __ll2float_rn(ia[1]) * inv_scale,
+                                 __ll2float_rn(ia[2]) * inv_scale, __ll2float_rn(ia[3]) * inv_scale);
+            } else {
+              *reinterpret_cast<longlong2*>(ap) = make_longlong2(ia[0], ia[1]);
+              *reinterpret_cast<longlong2*>(ap + 2) = make_longlong2(ia[2], ia[3]);
+            }
+          } else {
+            if (!first) {
+              const float4 o = *gxp;
+              acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+            }
+            *gxp = acc;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // channels-last gather.  One CTA = one 8 x 32 pixel tile, warp w owns tile row w and never waits for
 // another warp after the TMA barrier.  Every pixel of the row plays two roles:
 //   destination  grad-input[pixel] = sum over its contributor list of w * gout[source]
@@ -374,9 +746,6 @@ __global__ void __launch_bounds__(256) overflow_kernel(const BwdParams p) {
 //          unused list slots are filled with (own pixel, weight 0) so that phase 1 needs no predicates
 //          for the first four entries.
 // Phase 1: LP lanes at a time stream a pixel's float4 channel groups, NQ groups per lane per pass.
-__device__ __forceinline__ const float4* key_ptr(const char* base, int key) {
-  return reinterpret_cast<const float4*>(base + ((int64_t)(uint32_t)key << 4));  // keys count 16-byte units
-}
 
 // The destination role and the output role of a step are each split into "issue the loads" and "use
 // them", so that the fused kernel can put both roles' loads in flight before it waits for either.
@@ -403,7 +772,7 @@ __device__ __forceinline__ void gx_issue(const char* gl, int cnt, const int4& e0
 // NP pairs in all (pairs 0 and 1 arrive in e0 / e1, already loaded).
 template <int LP, int NQ, int NP>
 __device__ __forceinline__ void gx_finish(const char* gl, char* po, int cnt, const int4& e0, const int4& e1,
-                                          const int4* ent, int pstride, const float4 (&v)[4][NQ]) {
+                                          const int4* ent, int pstride, const float4 (&v)[4][NQ], bool store = true) {
   // slots past the count contribute nothing (their loads were predicated off): the accumulation is predicated too
   const float w[4] = {__int_as_float(e0.y), __int_as_float(e0.w), __int_as_float(e1.y), __int_as_float(e1.w)};
   float4 acc[NQ];
@@ -446,8 +815,10 @@ __device__ __forceinline__ void gx_finish(const char* gl, char* po, int cnt, con
       }
     }
   }
+  if (store) {  // (clear on "flex" tiles: gather_flex_kernel writes their grad-input)
 #pragma unroll
-  for (int q = 0; q < NQ; ++q) st_stream(reinterpret_cast<float4*>(po) + q * LP, acc[q]);
+    for (int q = 0; q < NQ; ++q) st_stream(reinterpret_cast<float4*>(po) + q * LP, acc[q]);
+  }
 }
 
 // Deterministic flavour of gx_finish: integer accumulation (see fixed_scale_from); `hot` destinations
@@ -637,27 +1008,47 @@ __global__ void __launch_bounds__(256, 4) gather_nhwc_kernel(const __grid_consta
       if (HAS_MASK) m = __ldg(p.mask + (int64_t)n * HW + pix);
     }
   }
+  // incoherent flows register single pixels with the destination tiles they touch (nreg of them here).  A few join the
+  // candidate segments in the local binning below; a HEAVY tile (clamped out-of-bounds flows pile thousands on the
+  // border tiles) gets its grad-input from gather_flex_kernel and this CTA only plays the output role (CTA-uniform)
+  // (both tile counters are requested here, side by side: they head the CTA's critical path)
+  // (deterministic mode only -- measured: for the float path the atomics of overflow_kernel are faster than the
+  // counting sort, profiles/r2_incoherent_flows.txt; compiled out of the ordinary gather, whose binning loop is the
+  // critical path of every CTA)
+  constexpr bool POOL = DET;
+  const int nreg = (POOL && DO_GX && p.bcount) ? __ldg(p.bcount + (n * tiles_y + by) * tiles_x + bx) : 0;
+  const int ncand_all = DO_GX ? __ldg(p.tcnt + (n * tiles_y + by) * tiles_x + bx) : 0;
+  const bool do_gx = DO_GX && (!POOL || nreg <= kFlexHeavy);
   if (DO_GX) {
     // ---- local binning: every warp walks candidate row segments (32 output pixels each), recomputes their
     // geometry and files the contributions that land inside this tile into the destination's list
     s_cnt[warp][lane] = 0;
     __syncthreads();
     const int T = (n * tiles_y + by) * tiles_x + bx;  // destination tile (n: image of x)
-    const int ncand = min(__ldg(p.tcnt + T), p.cand_cap);
+    const int ncand = do_gx ? min(ncand_all, p.cand_cap) : 0;
     const int2* tl = p.tlist + (int64_t)T * p.cand_cap;
     const int2 myid = (warp + 8 * lane < ncand) ? __ldg(tl + warp + 8 * lane) : make_int2(0, 0);  // warp w: c = w, w+8, ...
-    const int nit = (ncand - warp + 7) >> 3;
+    const int nit = max((ncand - warp + 7) >> 3, 0);
+    // registered pixels of incoherent segments: 32 at a time, warp w takes groups w, w + 8, ...
+    const int npool = (POOL && do_gx) ? nreg : 0, pool0 = npool ? __ldg(p.bstart + T) : 0;
+    const int nitp = POOL ? max((((npool + 31) >> 5) - warp + 7) >> 3, 0) : 0;
     const float det_scale = DET ? fixed_scale_from(__uint_as_float(p.maxbits[0]) * __uint_as_float(p.maxbits[1]),
                                                    p.count_log2) : 1.f;
 #pragma unroll 2
-    for (int it = 0; it < nit; ++it) {
-      const int seg0 = __shfl_sync(0xffffffffu, myid.x, it), nlive = __shfl_sync(0xffffffffu, myid.y, it);
+    for (int it = 0; it < nit + nitp; ++it) {
+      int sidx = -1;
+      if (!POOL || it < nit) {
+        const int seg0 = __shfl_sync(0xffffffffu, myid.x, it), nlive = __shfl_sync(0xffffffffu, myid.y, it);
+        if (lane < nlive) sidx = seg0 + lane;
+      } else {
+        const int v = (((it - nit) << 3) + warp) * 32 + lane;
+        if (v < npool) sidx = __ldg(p.pool + pool0 + v);
+      }
       // deterministic mode: contributions that found their list full (bit k), kept for the warp-wide push below
       unsigned failbits = 0;
       int f_pos = 0, f_sidx = 0;
       float f_ax = 0.f, f_ay = 0.f, f_m = 0.f;
-      if (lane < nlive) {
-        const int sidx = seg0 + lane;
+      if (sidx >= 0) {
         const int4 rec = __ldg(p.pixrec + sidx);
         const int ux0 = (int)(short)(rec.x & 0xffff), uy0 = rec.x >> 16;
         // tile-local position of the nw corner; the four corners are (dy, dx), (dy, dx+1), (dy+1, dx), (dy+1, dx+1)
@@ -724,7 +1115,37 @@ __global__ void __launch_bounds__(256, 4) gather_nhwc_kernel(const __grid_consta
     __syncthreads();
   }
   // (the lists stay where local binning put them: phase 1 clamps the count and ignores the slots past it)
-  if (DO_GX && DET && live && __ldcg(p.touched + (int64_t)n * HW + pix)) s_cnt[warp][lane] |= 0x40000000;
+  if (DO_GX && DET && live && do_gx) {
+    // Deterministic mode.  A destination whose terms all sit in its shared-memory list (no list overflow, nothing
+    // in the global accumulator) is summed in FLOAT over the list SORTED BY SOURCE: the set of (source, weight)
+    // entries is the same in every run, only their arrival order is not, so a fixed order gives fixed bits at the
+    // speed of the ordinary gather.  The rare "hot" destinations (bit 30) keep the order-independent integer sum.
+    // "Hot" is decided from run-independent quantities only -- WHICH contributions end up in the accumulator depends
+    // on the order of atomic slot claims, and a destination must take the same route in every run: more in-image
+    // corners point at it than a list holds (segbin_kernel's tally), a contribution was handed to overflow_kernel
+    // (tally bit 30: incoherent segments; failed registrations only happen in over-full tiles), its tile's candidate
+    // array is over-full, or its image has more incoherent segments than the clear-everything threshold.
+    const int c = s_cnt[warp][lane];
+    const int dc = __ldg(p.cnt + (int64_t)n * HW + pix);
+    const int T = (n * tiles_y + by) * tiles_x + bx;
+    if (dc > CAP || __ldg(p.tcnt + T) > p.cand_cap || __ldg(p.incoh + n) > p.incoh_thresh) {
+      // bit 29: the destination also has terms in the global accumulator row (that row was cleared for it)
+      s_cnt[warp][lane] = c | 0x40000000 | (__ldcg(p.touched + (int64_t)n * HW + pix) ? 0x20000000 : 0);
+    } else {
+      int2* const e = reinterpret_cast<int2*>(&s_ent[0][warp][lane]);  // slot k at e[(k >> 1) * (TH * TW * 2) + (k & 1)]
+      for (int a = 1; a < c; ++a) {  // insertion sort, 4 entries on average
+        const int2 key = e[(a >> 1) * (TH * TW * 2) + (a & 1)];
+        int b = a - 1;
+        while (b >= 0) {
+          const int2 o = e[(b >> 1) * (TH * TW * 2) + (b & 1)];
+          if ((unsigned)o.x <= (unsigned)key.x) break;
+          e[((b + 1) >> 1) * (TH * TW * 2) + ((b + 1) & 1)] = o;
+          --b;
+        }
+        e[((b + 1) >> 1) * (TH * TW * 2) + ((b + 1) & 1)] = key;
+      }
+    }
+  }
   if (DO_GF && USE_TMA) {
     mbar_wait(&bar, 0);
     fx = s_flow[0][warp][lane];
@@ -748,7 +1169,8 @@ __global__ void __launch_bounds__(256, 4) gather_nhwc_kernel(const __grid_consta
   const int nq = QI > 0 ? QI : ((p.cchunk >> 2) - lq + LP - 1) / LP;
   const float det_scale_m = (DET && DO_GX) ? fixed_scale_from(__uint_as_float(p.maxbits[0]) * __uint_as_float(p.maxbits[1]),
                                                               p.count_log2) : 1.f;
-  const float det_inv_m = 1.f / det_scale_m;  // a power of two: exact
+  // (a power of two: exact; NaN when gout holds a non-finite value)
+  const float det_inv_m = (DET && DO_GX) ? fixed_inv_scale(__uint_as_float(p.maxbits[0]) * __uint_as_float(p.maxbits[1]), det_scale_m) : 1.f;
   // blockIdx.y: channel slice of p.cchunk channels (small levels: more CTAs than tiles; every slice bins the
   // tile again, the slices' grad-flow / grad-mask partial sums are added by sum_parts_kernel)
   const uint32_t cb0 = blockIdx.y * (uint32_t)p.cchunk * 4u + lq * 16;
@@ -770,20 +1192,15 @@ __global__ void __launch_bounds__(256, 4) gather_nhwc_kernel(const __grid_consta
       DotRegs<NQ> dr;
       if (act) {
         if (DO_GX) {
-          cnt = min(s_cnt[warp][pa] & 0xffffff, CAP);
+          cnt = (DET && (s_cnt[warp][pa] & 0x40000000)) ? 0 : min(s_cnt[warp][pa] & 0xffffff, CAP);
           e0 = s_ent[0][warp][pa];
           e1 = s_ent[1][warp][pa];
           gx_issue<LP, NQ>(gl, cnt, e0, e1, v);
         }
         if (DO_GF) dot_issue_x<LP, NQ>(xl, s_off[warp][pa], dr);
-        if (DO_GX && DET) {
-          const bool hot = (s_cnt[warp][pa] & 0x40000000) != 0;
-          const long long* ha = p.acc64 + (rowpix + s) * (int64_t)d.C + lq * 4;
-          gx_finish_det<LP, NQ, NP>(gl, gxl, cnt, e0, e1, &s_ent[0][warp][pa], TH * TW, v, det_scale_m, det_inv_m,
-                                    hot ? ha : nullptr);
-        } else if (DO_GX) {
-          gx_finish<LP, NQ, NP>(gl, gxl, cnt, e0, e1, &s_ent[0][warp][pa], TH * TW, v);
-        }
+        // (deterministic mode: hot destinations are left to the integer pass after this loop)
+        if (DO_GX && !(DET && (s_cnt[warp][pa] & 0x40000000)))
+          gx_finish<LP, NQ, NP>(gl, gxl, cnt, e0, e1, &s_ent[0][warp][pa], TH * TW, v, do_gx);
         if (DO_GF) {
           // the pixel's own gout row (an L1 / L2 hit: its neighbours just gathered it) is fetched last, which
           // keeps the merged batch inside the register budget of four CTAs per SM (64 registers)
@@ -794,19 +1211,13 @@ __global__ void __launch_bounds__(256, 4) gather_nhwc_kernel(const __grid_consta
     } else if (act) {
 #pragma unroll 1
       for (int qi = 0; qi < nq; ++qi) {
-        if (DO_GX) {
+        if (DO_GX && !(DET && (s_cnt[warp][pa] & 0x40000000))) {
           const int cnt = min(s_cnt[warp][pa] & 0xffffff, CAP);
           const int4 e0 = s_ent[0][warp][pa], e1 = s_ent[1][warp][pa];
           float4 v[4][1];
           gx_issue<LP, 1>(gl + qi * (LP * 16), cnt, e0, e1, v);
-          if (DET) {
-            const bool hot = (s_cnt[warp][pa] & 0x40000000) != 0;
-            const long long* ha = p.acc64 + (rowpix + s) * (int64_t)d.C + (lq + qi * LP) * 4;
-            gx_finish_det<LP, 1, NP>(gl + qi * (LP * 16), gxl + qi * (LP * 16), cnt, e0, e1, &s_ent[0][warp][pa],
-                                     TH * TW, v, det_scale_m, det_inv_m, hot ? ha : nullptr);
-          } else {
-            gx_finish<LP, 1, NP>(gl + qi * (LP * 16), gxl + qi * (LP * 16), cnt, e0, e1, &s_ent[0][warp][pa], TH * TW, v);
-          }
+          gx_finish<LP, 1, NP>(gl + qi * (LP * 16), gxl + qi * (LP * 16), cnt, e0, e1, &s_ent[0][warp][pa], TH * TW, v,
+                               do_gx);
         }
         if (DO_GF) {
           DotRegs<1> dr;
@@ -823,6 +1234,32 @@ __global__ void __launch_bounds__(256, 4) gather_nhwc_kernel(const __grid_consta
     }
     if (DO_GX) gxl += G * pxb;
     gol += G * pxb;
+  }
+  if (DO_GX && DET && do_gx) {
+    // ---- deterministic mode, the hot destinations of this row: order-independent 64-bit fixed-point sums of the
+    // list entries, plus the accumulator row when other mechanisms added terms there (a separate pass: they are rare,
+    // and the float and the integer code never compete for registers)
+    if (__ballot_sync(0xffffffffu, live && (s_cnt[warp][lane] & 0x40000000))) {
+      char* gx0 = reinterpret_cast<char*>(p.gx) + rowpix * pxb + cb0;
+#pragma unroll 1
+      for (int s = 0; s < npx; s += G) {
+        const int pa = s + grp;
+        const int sc = ((G == 1) || (pa < npx)) ? s_cnt[warp][pa] : 0;
+        if (sc & 0x40000000) {
+          const int cnt = min(sc & 0xffffff, CAP);
+          const int4 e0 = s_ent[0][warp][pa], e1 = s_ent[1][warp][pa];
+#pragma unroll 1
+          for (int qi = 0; qi < nq; ++qi) {
+            float4 v[4][1];
+            gx_issue<LP, 1>(gl + qi * (LP * 16), cnt, e0, e1, v);
+            const long long* ha = p.acc64 + (rowpix + s) * (int64_t)d.C + (lq + qi * LP) * 4;
+            gx_finish_det<LP, 1, NP>(gl + qi * (LP * 16), gx0 + (int64_t)s * pxb + qi * (LP * 16), cnt, e0, e1,
+                                     &s_ent[0][warp][pa], TH * TW, v, det_scale_m, det_inv_m,
+                                     (sc & 0x20000000) ? ha : nullptr);
+          }
+        }
+      }
+    }
   }
   if (DO_GF) {
     __syncwarp();
@@ -1034,6 +1471,8 @@ static GatherWs carve(void* base, int64_t N, int H, int W, int64_t x_batch) {
 struct LocalWs {
   int* tcnt;
   int* ovf_count;
+  int *bcount, *bfill, *iseg_count, *flex_count, *flex_next;  // cleared with tcnt
+  int *bstart, *iseg_list, *flex_list, *pool;
   unsigned char* ovf;
   int2* tlist;
   int* ovf_list;
@@ -1067,7 +1506,12 @@ static LocalWs carve_local(void* base, int64_t N, int H, int W, int64_t x_batch,
   size_t o = 0;
   w.tcnt = reinterpret_cast<int*>(b + o);
   w.ovf_count = w.tcnt + ntile;
-  o += up256((ntile + 1) * sizeof(int));
+  w.bcount = w.ovf_count + 1;
+  w.bfill = w.bcount + ntile;
+  w.iseg_count = w.bfill + ntile;
+  w.flex_count = w.iseg_count + 1;
+  w.flex_next = w.flex_count + 1;
+  o += up256((3 * ntile + 4) * sizeof(int));
   w.ovf = reinterpret_cast<unsigned char*>(b + o);
   w.ovf_stride = up256(npix_o);
   o += nov * w.ovf_stride;
@@ -1078,6 +1522,14 @@ static LocalWs carve_local(void* base, int64_t N, int H, int W, int64_t x_batch,
   o += up256(nov * npix_o * sizeof(int));
   w.pixrec = reinterpret_cast<int4*>(b + o);
   o += up256(npix_o * sizeof(int4));
+  w.bstart = reinterpret_cast<int*>(b + o);
+  o += up256(ntile * sizeof(int));
+  w.flex_list = reinterpret_cast<int*>(b + o);
+  o += up256(ntile * sizeof(int));
+  w.iseg_list = reinterpret_cast<int*>(b + o);
+  o += up256((size_t)N * H * ((W + 31) / 32) * sizeof(int));
+  w.pool = reinterpret_cast<int*>(b + o);
+  o += up256(4 * npix_o * sizeof(int));
   w.gpart = nullptr;
   w.slices = slices;
   if (small) {
@@ -1155,6 +1607,15 @@ __global__ void __launch_bounds__(256) sum_parts_kernel(const float* __restrict_
   } else if (gmask) {
     gmask[k - nflow] = s;
   }
+}
+
+// C2M_WARP_FLEX=0: incoherent segments take the overflow list (atomics) instead of the per-tile counting sort
+static bool flex_enabled() {
+  static const bool v = [] {
+    const char* e = getenv("C2M_WARP_FLEX");
+    return !(e && *e == '0');
+  }();
+  return v;
 }
 
 template <int LP, int QI, bool DO_GX, bool DO_GF, bool DET>
@@ -1240,12 +1701,14 @@ __global__ void __launch_bounds__(256) absmax_flat_kernel(const float* __restric
   const float4* a4 = reinterpret_cast<const float4*>(a);
   for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n4; k += (int64_t)gridDim.x * blockDim.x) {
     const float4 v = __ldg(a4 + k);
+    // (fmaxf drops a NaN operand: test the sum, which is NaN as soon as one element is)
     const float m4 = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
-    mx = (m4 == m4) ? fmaxf(mx, m4) : mx;
+    const float chk = v.x + v.y + v.z + v.w;
+    mx = (chk == chk) ? fmaxf(mx, m4) : __int_as_float(0x7f800000);
   }
   for (int64_t k = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
     const float v = fabsf(a[k]);
-    mx = (v == v) ? fmaxf(mx, v) : mx;
+    mx = (v == v) ? fmaxf(mx, v) : __int_as_float(0x7f800000);  // NaN counts as +inf: "non-finite seen"
   }
   for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   if ((threadIdx.x & 31) == 0 && mx > 0.f) atomicMax(out_bits, __float_as_uint(mx));
@@ -1274,6 +1737,9 @@ int launch_bwd_gather(const BwdParams& pin, Layout lx, void* workspace, size_t w
       return C2M_ERR_WORKSPACE;
     }
     p.tcnt = w.tcnt;
+    p.bcount = w.bcount; p.bstart = w.bstart; p.bfill = w.bfill; p.pool = w.pool;
+    p.iseg_count = w.iseg_count; p.iseg_list = w.iseg_list;
+    p.flex_count = w.flex_count; p.flex_list = w.flex_list; p.flex_next = w.flex_next;
     p.tlist = w.tlist;
     p.cand_cap = w.cand_cap;
     p.pixrec = w.pixrec;
@@ -1304,9 +1770,20 @@ int launch_bwd_gather(const BwdParams& pin, Layout lx, void* workspace, size_t w
       else set_bits_kernel<<<1, 1, 0, st>>>(w.maxbits + 1, 0x3f800000u);
       count_launch(2);
     }
+    // the counting sort of incoherent segments serves the deterministic mode (it replaces 64-bit atomics per
+    // contribution); the float path keeps overflow_kernel's vector reductions, which are faster than the sort
+    if (!det || !flex_enabled()) p.bcount = nullptr;
     const int segs = d.H * ((d.W + 31) / 32);  // per frame; grid.y = frames (N <= 65535 checked by gather_supported)
     segbin_kernel<<<dim3((unsigned)((segs + 7) / 8), (unsigned)d.N), 256, 0, st>>>(p);
     count_launch();
+    if (p.bcount) {
+      // incoherent flows: finish the counting sort of their pixels by destination tile (both kernels leave at once
+      // when segbin_kernel met no incoherent segment)
+      const int ntile = d.x_batch * ((d.H + 7) / 8) * ((d.W + 31) / 32);
+      flex_scan_kernel<<<1, 1024, 0, st>>>(p, ntile);
+      flex_fill_kernel<<<sm_count() * 8, 256, 0, st>>>(p);
+      count_launch(2);
+    }
     if (det) {  // incoherent segments / failed registrations first: the gather folds their rows in
       const int64_t ndest = (int64_t)d.x_batch * d.H * d.W;
       zero_hot_rows_kernel<<<(unsigned)((ndest + 255) / 256), 256, 0, st>>>(w.dcnt, w.incoh, p.incoh_thresh, w.acc64,
@@ -1357,6 +1834,16 @@ int launch_bwd_gather(const BwdParams& pin, Layout lx, void* workspace, size_t w
     if (need_gf) launch_gather_nchw<false, true, false>(p, st);
   }
   profile_end(st);
+  if (p.gx && local && p.bcount) {
+    const int C4 = d.C / 4, grid = sm_count() * 4;
+#define C2M_FLEX(LP) gather_flex_kernel<LP, true><<<grid, 256, 0, st>>>(p)  /* (bcount is only set in deterministic mode) */
+    if (C4 >= 32) C2M_FLEX(32);
+    else if (C4 >= 16) C2M_FLEX(16);
+    else if (C4 >= 8) C2M_FLEX(8);
+    else C2M_FLEX(4);
+#undef C2M_FLEX
+    count_launch();
+  }
   if (p.gx && !(local && det)) {
     const int grid = sm_count() * 8;
     if (lx == LAYOUT_NHWC)  // gather_supported() has checked C % 4 and the 16-byte alignment

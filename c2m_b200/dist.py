@@ -42,11 +42,21 @@ def init(backend: str | None = None) -> Tuple[int, int, int]:
     return rank, local_rank, world
 
 
+def _reduce_device(device):
+    """Where the one-element reduce tensor lives: NCCL reduces CUDA tensors only (the rank's current device), gloo
+    takes CPU tensors."""
+    if device is not None:
+        return device
+    if dist.get_backend() == "nccl":
+        return torch.device("cuda", torch.cuda.current_device())
+    return "cpu"
+
+
 def max_over_ranks(value: float, device=None) -> float:
     """Max of a per-rank scalar (device-timed milliseconds) over all ranks."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return float(value)
-    t = torch.tensor([float(value)], dtype=torch.float64, device=device or "cpu")
+    t = torch.tensor([float(value)], dtype=torch.float64, device=_reduce_device(device))
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
 
@@ -54,7 +64,7 @@ def max_over_ranks(value: float, device=None) -> float:
 def sum_over_ranks(value: float, device=None) -> float:
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return float(value)
-    t = torch.tensor([float(value)], dtype=torch.float64, device=device or "cpu")
+    t = torch.tensor([float(value)], dtype=torch.float64, device=_reduce_device(device))
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return float(t.item())
 

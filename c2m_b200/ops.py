@@ -46,14 +46,24 @@ def grid_sample(input1: torch.Tensor, input2: torch.Tensor, mode: str = "bilinea
 
 
 class _GridSampleFunction(torch.autograd.Function):
+    # under autocast the op runs in float32 with its inputs cast up, like WarpBlendFunction
     @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(ctx, image, grid):
+        if not (image.is_cuda and grid.is_cuda):
+            raise RuntimeError("c2m_b200.grid_sample: CUDA tensors required (no CPU fallback)")
+        if image.dtype != torch.float32 or grid.dtype != torch.float32:
+            raise TypeError(f"c2m_b200.grid_sample: float32 tensors required, got {image.dtype} and {grid.dtype}")
+        if image.device != grid.device:
+            raise RuntimeError("c2m_b200.grid_sample: all tensors must be on the same device")
+        if image.dim() != 4:
+            raise ValueError(f"expected an image [B,C,H,W], got {tuple(image.shape)}")
+        if image.shape[0] != grid.shape[0] and (image.shape[0] == 0 or grid.shape[0] % image.shape[0] != 0):
+            raise ValueError(f"image batch {image.shape[0]} must equal or divide the grid batch {grid.shape[0]}")
         x = image.contiguous()
         g = grid.contiguous()  # [N,H,W,2]; the kernels take it through the `flow` slot
         N, H, W, _ = g.shape
         C = x.shape[1]
-        if not (x.is_cuda and g.is_cuda) or x.dtype != torch.float32 or g.dtype != torch.float32:
-            raise RuntimeError("c2m_b200.grid_sample: float32 CUDA tensors required (no CPU fallback)")
         out = torch.empty((N, C, H, W), dtype=x.dtype, device=x.device)
         with torch.cuda.device(x.device):
             _lib.warp_blend_fwd(x.data_ptr(), g.data_ptr(), None, None, out.data_ptr(), N, C, H, W, x.shape[0],
@@ -64,6 +74,7 @@ class _GridSampleFunction(torch.autograd.Function):
 
     @staticmethod
     @torch.autograd.function.once_differentiable
+    @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, gout):
         x, g = ctx.saved_tensors
         gout = gout.contiguous()

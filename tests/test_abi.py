@@ -86,7 +86,7 @@ def test_workspace_size_contract():
     #  NCHW global lists: per destination pixel a 4 B counter (+ the overflow-list length and one per-frame
     #  "tiles binned" counter behind the counters) and 8 in-line (src, w) entries; per output pixel a 1 B
     #  overflow flag and a 4 B overflow-list slot; each block rounded up to 256 B.
-    #  channels-last local binning: tile counters, overflow flags, candidate segments (8 B each, 96 per tile and
+    #  channels-last local binning: tile counters (candidates, registrations, fill cursors), overflow flags, candidate segments (8 B each, 96 per tile and
     #  source frame), overflow list, 16 B pixel records; levels with fewer than 1184 tiles (8 per SM) and at least
     #  128 channels are channel-sliced (2, 4 or 8 slices of >= 64 channels): 1 + slices flag arrays / list segments
     #  and one grad-flow / grad-mask partial-sum buffer per slice.
@@ -105,7 +105,10 @@ def test_workspace_size_contract():
                and c4 // 2 >= 16):
             slices, c4 = slices * 2, c4 // 2
         nov = 1 + slices if slices > 1 else 1
-        v = up(4 * (ntile + 1)) + nov * up(npo) + up(8 * ntile * cap) + up(4 * nov * npo) + up(16 * npo)
+        v = up(4 * (3 * ntile + 4)) + nov * up(npo) + up(8 * ntile * cap) + up(4 * nov * npo) + up(16 * npo)
+        # incoherent flows (counting sort of their pixels by destination tile): tile offsets, flex-tile list, the
+        # list of incoherent segments, and the pool of registered pixels (at most four tiles per pixel)
+        v += 2 * up(4 * ntile) + up(4 * N * H * ((W + 31) // 32)) + up(16 * npo)
         if slices > 1:
             v += up(slices * 3 * npo * 4)
         if det:  # + scale bits, touched flags, per-destination corner counts, per-image incoherent-segment counters and the int64 overflow rows

@@ -551,3 +551,23 @@ def test_full_resolution_shard_parity(dev):
     d2 = torch.autograd.grad(c2m_b200.warp_blend(xr, fr, mr, deterministic=True), [xr], gout)[0]
     assert torch.equal(d1, d2)
     assert rel(d1[0:1], gx[0:1]) <= GRAD_TOL and rel(d1[7:8], gx[7:8]) <= GRAD_TOL
+
+
+def test_deterministic_mode_propagates_nonfinite_gradients(dev):
+    """the integer sums of the deterministic mode cannot carry NaN / inf; destinations summed that way
+    are poisoned as a whole when the upstream gradient holds a non-finite value (the float-summed ones propagate it
+    like ATen) -- nothing that the reference reports as non-finite comes back finite."""
+    x, flow, mask, gout = make_inputs(dev, 2, 16, 32, 64, seed=41)
+    jj = torch.arange(64, device=dev, dtype=torch.float32).view(1, 1, -1)
+    ii = torch.arange(32, device=dev, dtype=torch.float32).view(1, -1, 1)
+    flow[:, 0] = (32 - jj) * 0.9 + torch.randn_like(flow[:, 0])  # converging: long lists, list overflow
+    flow[:, 1] = (16 - ii) * 0.9 + torch.randn_like(flow[:, 1])
+    gout[0, 3, 10, 20] = float("inf")
+    gout[1, 5, 16, 32] = float("nan")
+    for layout in ("nchw", "nhwc"):
+        xl = x.contiguous(memory_format=torch.channels_last) if layout == "nhwc" else x
+        ours = run_ours(xl, flow, mask, gout, deterministic=True)[1][0]
+        ref = run_ref(x, flow, mask, gout)[1][0]
+        bad_ref = ~torch.isfinite(ref)
+        assert bad_ref.any()
+        assert (~torch.isfinite(ours))[bad_ref].all(), layout
