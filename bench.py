@@ -527,10 +527,35 @@ def run_ours(args):
             e2e_steps = max(1, min(args.steps, args.e2e_steps))
             ems, et0, et1 = _time_steps(lambda: plan.run(hx, hflow, hmask, hgout), e2e_steps, 2, barrier)
             e2e_value, _, _ = cdist.aggregate_throughput(N * e2e_steps, ems * e2e_steps, dev)
+            plan_bytes_per_frame = plan.h2d_bytes / N
             e2e = {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": plan.h2d_bytes,
                    "d2h_bytes_per_step": plan.d2h_bytes, "steps": e2e_steps, "chunks": plan.chunks,
-                   "pcie_gbs_each_way": plan.h2d_bytes / (ems * 1e-3) / 1e9, "clocks": clk.window(et0, et1)}
-            del plan, hx, hflow, hmask, hgout
+                   "pcie_gbs_each_way": e2e_value / world * plan.h2d_bytes / N / 1e9, "clocks": clk.window(et0, et1)}
+            del plan
+            # the ceiling this figure lives under: pinned host <-> device copies of the same tensors, both directions
+            # at once on two streams, nothing else -- measured by every rank at the same time (the ranks of one box
+            # share the host memory system and the PCIe root complexes)
+            dx, dg = torch.empty_like(hx, device=dev), torch.empty_like(hgout, device=dev)
+            s_up, s_down = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+            def both_ways():
+                cur = torch.cuda.current_stream(dev)
+                s_up.wait_stream(cur)
+                s_down.wait_stream(cur)
+                with torch.cuda.stream(s_up):
+                    dx.copy_(hx, non_blocking=True)
+                with torch.cuda.stream(s_down):
+                    hgout.copy_(dg, non_blocking=True)
+                cur.wait_stream(s_up)
+                cur.wait_stream(s_down)
+
+            cms, _, _ = _time_steps(both_ways, 5, 2, barrier)
+            cms = cdist.max_over_ranks(cms, dev)
+            ceil_gbs = hx.numel() * 4 / (cms * 1e-3) / 1e9
+            e2e["pcie_ceiling_gbs_each_way"] = ceil_gbs
+            # per-rank bytes per second each way in the e2e run, over the per-rank ceiling under the same concurrency
+            e2e["frac_of_pcie_ceiling"] = (e2e_value / world * plan_bytes_per_frame / 1e9) / ceil_gbs
+            del dx, dg, hx, hflow, hmask, hgout
 
         # ---- the dominant kernels alone: the library brackets its forward kernel / backward gather kernel with
         # CUDA events on the launching stream (c2m_warp_profile); read back after each call, outside the timed region

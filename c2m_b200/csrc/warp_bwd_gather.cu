@@ -163,18 +163,18 @@ __global__ void __launch_bounds__(256) segbin_kernel(const BwdParams p) {
   // receive terms outside their 12-entry list (a per-tile mark written with plain stores instead of the
   // bit-30 atomics was tried: the reads of the small mark array hot-spot L2 and it is slower)
   bool all_hot = false;  // this image already has so many incoherent segments that all its rows get cleared
-  auto tally = [&](unsigned ovfbits) {
+  auto tally = [&](unsigned ovfbits) {  // (every lane of the warp calls it, at warp-uniform places)
     if (!p.cnt) return;
     int* c0 = p.cnt + (n % d.x_batch) * HW;
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-      if (inimg & (1u << k)) {
-        if (ovfbits & (1u << k)) {
-          if (!all_hot) atomicOr(c0 + ys[k] * d.W + xs[k], 0x40000000);  // (counts stay below 2^30)
-        } else {
-          atomicAdd(c0 + ys[k] * d.W + xs[k], 1);
-        }
-      }
+    for (int k = 0; k < 4; ++k) {
+      const bool in = (inimg & (1u << k)) != 0, ov = (ovfbits & (1u << k)) != 0;
+      if (in && ov && !all_hot) atomicOr(c0 + ys[k] * d.W + xs[k], 0x40000000);  // (counts stay below 2^30)
+      // clamped out-of-bounds flows point whole segments at one border pixel: one atomic per distinct destination
+      const int key = (in && !ov) ? ys[k] * d.W + xs[k] : -1;
+      const unsigned peers = __match_any_sync(0xffffffffu, key);
+      if (key >= 0 && lane == __ffs(peers) - 1) atomicAdd(c0 + key, __popc(peers));
+    }
   };
   if (live) {
     const float* fl = p.flow + (int64_t)n * 2 * HW + i * d.W + j;
@@ -1019,6 +1019,14 @@ __global__ void __launch_bounds__(256, 4) gather_nhwc_kernel(const __grid_consta
   const int nreg = (POOL && DO_GX && p.bcount) ? __ldg(p.bcount + (n * tiles_y + by) * tiles_x + bx) : 0;
   const int ncand_all = DO_GX ? __ldg(p.tcnt + (n * tiles_y + by) * tiles_x + bx) : 0;
   const bool do_gx = DO_GX && (!POOL || nreg <= kFlexHeavy);
+  // deterministic mode: what decides whether this thread's destination pixel is "hot" (below) is requested now, so that
+  // the answers are there when the binning is done (they used to sit on the CTA's critical path)
+  int det_dc = 0, det_incoh = 0;
+  if (DET && DO_GX && live) {
+    det_dc = __ldg(p.cnt + (int64_t)n * HW + pix);
+    det_incoh = __ldg(p.incoh + n);
+  }
+  bool det_pushed = false;  // this warp added terms to the global accumulator (list overflow)
   if (DO_GX) {
     // ---- local binning: every warp walks candidate row segments (32 output pixels each), recomputes their
     // geometry and files the contributions that land inside this tile into the destination's list
@@ -1088,6 +1096,7 @@ __global__ void __launch_bounds__(256, 4) gather_nhwc_kernel(const __grid_consta
         // fixed-point row (lanes across channels) and marks the destination; phase 1 of this same CTA
         // picks the row up before it converts
         unsigned any = __ballot_sync(0xffffffffu, failbits != 0u);
+        det_pushed |= any != 0u;
         while (any) {
           const int src = __ffs(any) - 1;
           any &= any - 1;
@@ -1111,7 +1120,7 @@ __global__ void __launch_bounds__(256, 4) gather_nhwc_kernel(const __grid_consta
         }
       }
     }
-    if (DET) __threadfence();
+    if (DET && det_pushed) __threadfence();  // the pushed terms and marks are visible to the CTA's other warps
     __syncthreads();
   }
   // (the lists stay where local binning put them: phase 1 clamps the count and ignores the slots past it)
@@ -1126,9 +1135,7 @@ __global__ void __launch_bounds__(256, 4) gather_nhwc_kernel(const __grid_consta
     // (tally bit 30: incoherent segments; failed registrations only happen in over-full tiles), its tile's candidate
     // array is over-full, or its image has more incoherent segments than the clear-everything threshold.
     const int c = s_cnt[warp][lane];
-    const int dc = __ldg(p.cnt + (int64_t)n * HW + pix);
-    const int T = (n * tiles_y + by) * tiles_x + bx;
-    if (dc > CAP || __ldg(p.tcnt + T) > p.cand_cap || __ldg(p.incoh + n) > p.incoh_thresh) {
+    if (det_dc > CAP || ncand_all > p.cand_cap || det_incoh > p.incoh_thresh) {
       // bit 29: the destination also has terms in the global accumulator row (that row was cleared for it)
       s_cnt[warp][lane] = c | 0x40000000 | (__ldcg(p.touched + (int64_t)n * HW + pix) ? 0x20000000 : 0);
     } else {
