@@ -106,38 +106,117 @@ __global__ void __launch_bounds__(TH* TW, (TH * TW <= 256) ? 768 / (TH * TW) : 2
       const float* psw = xc + (g.y1 * d.W + g.x0);
       const float* pse = xc + (g.y1 * d.W + g.x1);
       float* oc = p.out + ((int64_t)n * d.C + c0) * HW + i * d.W + j;
-      // blend operand (out = m*warp + (1-m)*other): read at the output position, same strides as `out`
-      const float* otc = p.other ? p.other + ((int64_t)n * d.C + c0) * HW + i * d.W + j : nullptr;
-      const float om = 1.f - m;
+      // blend operand (out = m*warp + (1-m)*other): read at the output position, same strides as `out`.  Its own
+      // copy of the channel loop: the plain loop stays exactly as it was (it is latency-bound on its four gathers
+      // per channel and loses a third of its speed to any extra work in the body)
+      const float* otc = (HAS_MASK && p.other) ? p.other + ((int64_t)n * d.C + c0) * HW + i * d.W + j : nullptr;
+      if (otc) {
+        const float om = 1.f - m;
 #pragma unroll UNROLL
-      for (int c = 0; c < nc; ++c) {
-        float vnw = __ldg(pnw), vne = __ldg(pne);
-        float vsw = __ldg(psw), vse = __ldg(pse);
-        vnw = g.oknw ? vnw : 0.f;
-        vne = g.okne ? vne : 0.f;
-        vsw = g.oksw ? vsw : 0.f;
-        vse = g.okse ? vse : 0.f;
-        float acc = vnw * g.wnw;
-        acc = fmaf(vne, g.wne, acc);
-        acc = fmaf(vsw, g.wsw, acc);
-        acc = fmaf(vse, g.wse, acc);
-        float o = HAS_MASK ? __fmul_rn(acc, m) : acc;
-        if (HAS_MASK && otc) {
-          o = __fadd_rn(o, __fmul_rn(om, __ldg(otc)));
+        for (int c = 0; c < nc; ++c) {
+          float vnw = __ldg(pnw), vne = __ldg(pne);
+          float vsw = __ldg(psw), vse = __ldg(pse);
+          const float ot = __ldg(otc);
+          vnw = g.oknw ? vnw : 0.f;
+          vne = g.okne ? vne : 0.f;
+          vsw = g.oksw ? vsw : 0.f;
+          vse = g.okse ? vse : 0.f;
+          float acc = vnw * g.wnw;
+          acc = fmaf(vne, g.wne, acc);
+          acc = fmaf(vsw, g.wsw, acc);
+          acc = fmaf(vse, g.wse, acc);
+          st_stream(oc, __fadd_rn(__fmul_rn(acc, m), __fmul_rn(om, ot)));
+          pnw += HW;
+          pne += HW;
+          psw += HW;
+          pse += HW;
+          oc += HW;
           otc += HW;
         }
-        st_stream(oc, o);
-        pnw += HW;
-        pne += HW;
-        psw += HW;
-        pse += HW;
-        oc += HW;
+      } else {
+#pragma unroll UNROLL
+        for (int c = 0; c < nc; ++c) {
+          float vnw = __ldg(pnw), vne = __ldg(pne);
+          float vsw = __ldg(psw), vse = __ldg(pse);
+          vnw = g.oknw ? vnw : 0.f;
+          vne = g.okne ? vne : 0.f;
+          vsw = g.oksw ? vsw : 0.f;
+          vse = g.okse ? vse : 0.f;
+          float acc = vnw * g.wnw;
+          acc = fmaf(vne, g.wne, acc);
+          acc = fmaf(vsw, g.wsw, acc);
+          acc = fmaf(vse, g.wse, acc);
+          st_stream(oc, HAS_MASK ? __fmul_rn(acc, m) : acc);
+          pnw += HW;
+          pne += HW;
+          psw += HW;
+          pse += HW;
+          oc += HW;
+        }
       }
     }
     if (USE_TMA) {
       __syncthreads();  // every thread has consumed buffer `buf` before it is refilled
       buf ^= 1;
     }
+  }
+}
+
+// The row loop of fwd_nhwc_kernel: LP lanes at a time stream a pixel's float4 channel groups.
+template <int LP, int QI, bool HAS_MASK, bool OTHER>
+__device__ __forceinline__ void fwd_nhwc_rows(const uint4* __restrict__ off_row, const float4* __restrict__ w_row,
+                                              const float2* __restrict__ mk_row, const char* xl, char* ol,
+                                              int64_t ot_delta, int npx, int grp, int nq, uint32_t pxb) {
+  constexpr int G = 32 / LP;
+#pragma unroll 1
+  for (int s = 0; s < npx; s += G) {
+    const int pa = s + grp;
+    if (G == 1 || pa < npx) {
+      const uint4 off = off_row[pa];
+      const float4 w = w_row[pa];
+      const float2 mk = mk_row[pa];
+      const int ok = __float_as_int(mk.y);
+      const char* px = xl;
+      char* po = ol;
+#pragma unroll 1
+      for (int qi = 0; qi < (QI > 0 ? QI : nq); ++qi) {
+        float4 a = ldg_batch(reinterpret_cast<const float4*>(px + off.x));
+        float4 b = ldg_batch(reinterpret_cast<const float4*>(px + off.y));
+        float4 c = ldg_batch(reinterpret_cast<const float4*>(px + off.z));
+        float4 e = ldg_batch(reinterpret_cast<const float4*>(px + off.w));
+        float4 ot = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (OTHER) ot = ldg_batch(reinterpret_cast<const float4*>(po + ot_delta));
+        if (ok != 15) {  // a corner outside the image (zeros padding / exact border hits)
+          const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (!(ok & 1)) a = z;
+          if (!(ok & 2)) b = z;
+          if (!(ok & 4)) c = z;
+          if (!(ok & 8)) e = z;
+        }
+        float4 o;
+        o.x = fmaf(e.x, w.w, fmaf(c.x, w.z, fmaf(b.x, w.y, a.x * w.x)));
+        o.y = fmaf(e.y, w.w, fmaf(c.y, w.z, fmaf(b.y, w.y, a.y * w.x)));
+        o.z = fmaf(e.z, w.w, fmaf(c.z, w.z, fmaf(b.z, w.y, a.z * w.x)));
+        o.w = fmaf(e.w, w.w, fmaf(c.w, w.z, fmaf(b.w, w.y, a.w * w.x)));
+        if (HAS_MASK) {
+          o.x = __fmul_rn(o.x, mk.x);
+          o.y = __fmul_rn(o.y, mk.x);
+          o.z = __fmul_rn(o.z, mk.x);
+          o.w = __fmul_rn(o.w, mk.x);
+          if (OTHER) {  // out = m*warp + (1-m)*other
+            const float om = 1.f - mk.x;
+            o.x = __fadd_rn(o.x, __fmul_rn(om, ot.x));
+            o.y = __fadd_rn(o.y, __fmul_rn(om, ot.y));
+            o.z = __fadd_rn(o.z, __fmul_rn(om, ot.z));
+            o.w = __fadd_rn(o.w, __fmul_rn(om, ot.w));
+          }
+        }
+        st_stream(reinterpret_cast<float4*>(po), o);
+        px += LP * 16;
+        po += LP * 16;
+      }
+    }
+    ol += G * pxb;
   }
 }
 
@@ -227,55 +306,11 @@ __global__ void __launch_bounds__(256, 6) fwd_nhwc_kernel(const __grid_constant_
   // blend operand (out = m*warp + (1-m)*other): the pixel's own row of `other`, same layout as `out`
   const int64_t ot_delta = (HAS_MASK && p.other) ? reinterpret_cast<const char*>(p.other) - reinterpret_cast<const char*>(p.out) : 0;
   const int nq = QI > 0 ? QI : (C4 - lq + LP - 1) / LP;  // float4 groups of this lane
-#pragma unroll 1
-  for (int s = 0; s < npx; s += G) {
-    const int pa = s + grp;
-    if (G == 1 || pa < npx) {
-      const uint4 off = s_off[warp][pa];
-      const float4 w = s_w[warp][pa];
-      const float2 mk = s_mk[warp][pa];
-      const int ok = __float_as_int(mk.y);
-      const char* px = xl;
-      char* po = ol;
-#pragma unroll 1
-      for (int qi = 0; qi < (QI > 0 ? QI : nq); ++qi) {
-        float4 a = ldg_batch(reinterpret_cast<const float4*>(px + off.x));
-        float4 b = ldg_batch(reinterpret_cast<const float4*>(px + off.y));
-        float4 c = ldg_batch(reinterpret_cast<const float4*>(px + off.z));
-        float4 e = ldg_batch(reinterpret_cast<const float4*>(px + off.w));
-        if (ok != 15) {  // a corner outside the image (zeros padding / exact border hits)
-          const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (!(ok & 1)) a = z;
-          if (!(ok & 2)) b = z;
-          if (!(ok & 4)) c = z;
-          if (!(ok & 8)) e = z;
-        }
-        float4 o;
-        o.x = fmaf(e.x, w.w, fmaf(c.x, w.z, fmaf(b.x, w.y, a.x * w.x)));
-        o.y = fmaf(e.y, w.w, fmaf(c.y, w.z, fmaf(b.y, w.y, a.y * w.x)));
-        o.z = fmaf(e.z, w.w, fmaf(c.z, w.z, fmaf(b.z, w.y, a.z * w.x)));
-        o.w = fmaf(e.w, w.w, fmaf(c.w, w.z, fmaf(b.w, w.y, a.w * w.x)));
-        if (HAS_MASK) {
-          o.x = __fmul_rn(o.x, mk.x);
-          o.y = __fmul_rn(o.y, mk.x);
-          o.z = __fmul_rn(o.z, mk.x);
-          o.w = __fmul_rn(o.w, mk.x);
-          if (ot_delta != 0) {
-            const float4 ot = ldg_batch(reinterpret_cast<const float4*>(po + ot_delta));
-            const float om = 1.f - mk.x;
-            o.x = __fadd_rn(o.x, __fmul_rn(om, ot.x));
-            o.y = __fadd_rn(o.y, __fmul_rn(om, ot.y));
-            o.z = __fadd_rn(o.z, __fmul_rn(om, ot.z));
-            o.w = __fadd_rn(o.w, __fmul_rn(om, ot.w));
-          }
-        }
-        st_stream(reinterpret_cast<float4*>(po), o);
-        px += LP * 16;
-        po += LP * 16;
-      }
-    }
-    ol += G * pxb;
-  }
+  // (the blend operand gets its own copy of the row loop: the plain one stays as lean as it was)
+  if (ot_delta != 0)
+    fwd_nhwc_rows<LP, QI, HAS_MASK, true>(s_off[warp], s_w[warp], s_mk[warp], xl, ol, ot_delta, npx, grp, nq, pxb);
+  else
+    fwd_nhwc_rows<LP, QI, HAS_MASK, false>(s_off[warp], s_w[warp], s_mk[warp], xl, ol, 0, npx, grp, nq, pxb);
 }
 
 // ---------------------------------------------------------------------------------------------
