@@ -948,7 +948,9 @@ __global__ void __launch_bounds__(256, 4) gather_nhwc_kernel(const __grid_consta
                                                              const __grid_constant__ CUtensorMap tm_mask) {
   constexpr int TH = 8, TW = 32;
   constexpr int G = 32 / LP;
-  constexpr int CAP = kLocalCap;  // entries per destination held in shared memory
+  // entries per destination held in shared memory.  Deterministic mode takes 16: a list overflow there is pushed to
+  // the global accumulator by the discovering warp (64-bit atomics per channel) while its CTA waits at the barrier
+  constexpr int CAP = DET ? kLocalCapDet : kLocalCap;
   constexpr int NP = CAP / 2;                        // as int4 entry pairs
   __shared__ alignas(128) float s_flow[DO_GF ? 2 : 1][TH][TW];
   __shared__ alignas(128) float s_mask[TH][TW];
@@ -957,7 +959,9 @@ __global__ void __launch_bounds__(256, 4) gather_nhwc_kernel(const __grid_consta
   // ax, ay, mask, flags (bits 0-3: corner inside the image, 4 / 5: x / y coordinate clipped -> zero
   // grad-flow); later the pixel's (gflow_x, gflow_y, gmask)
   __shared__ float4 s_aux[DO_GF ? TH : 1][TW];
-  __shared__ float4 s_sum[DO_GF ? TH : 1][TW];  // the pixel's four dot products sum_c gout[c] * x_corner[c]
+  // the pixel's four dot products sum_c gout[c] * x_corner[c].  (Deterministic mode, which spends its shared memory on
+  // longer lists, parks them in the pixel's corner offsets instead: those are dead once its step has issued its loads.)
+  __shared__ float4 s_sum[(DO_GF && !DET) ? TH : 1][TW];
   __shared__ int s_cnt[DO_GX ? TH : 1][TW];
   __shared__ int4 s_ent[DO_GX ? NP : 1][DO_GX ? TH : 1][TW];
   const Dims& d = p.d;
@@ -1026,7 +1030,6 @@ __global__ void __launch_bounds__(256, 4) gather_nhwc_kernel(const __grid_consta
     det_dc = __ldg(p.cnt + (int64_t)n * HW + pix);
     det_incoh = __ldg(p.incoh + n);
   }
-  bool det_pushed = false;  // this warp added terms to the global accumulator (list overflow)
   if (DO_GX) {
     // ---- local binning: every warp walks candidate row segments (32 output pixels each), recomputes their
     // geometry and files the contributions that land inside this tile into the destination's list
@@ -1096,7 +1099,6 @@ __global__ void __launch_bounds__(256, 4) gather_nhwc_kernel(const __grid_consta
         // fixed-point row (lanes across channels) and marks the destination; phase 1 of this same CTA
         // picks the row up before it converts
         unsigned any = __ballot_sync(0xffffffffu, failbits != 0u);
-        det_pushed |= any != 0u;
         while (any) {
           const int src = __ffs(any) - 1;
           any &= any - 1;
@@ -1120,7 +1122,9 @@ __global__ void __launch_bounds__(256, 4) gather_nhwc_kernel(const __grid_consta
         }
       }
     }
-    if (DET && det_pushed) __threadfence();  // the pushed terms and marks are visible to the CTA's other warps
+    // (deterministic mode: the terms and marks a warp pushed to global memory are only ever read by THIS CTA, after
+    // this barrier, with L1-bypassing loads -- __syncthreads() orders them; a device-wide fence here cost an L1
+    // invalidation per pushing warp, CCTL.IVALL, and with it the gather's L1 hit rate)
     __syncthreads();
   }
   // (the lists stay where local binning put them: phase 1 clamps the count and ignores the slots past it)
@@ -1237,7 +1241,7 @@ __global__ void __launch_bounds__(256, 4) gather_nhwc_kernel(const __grid_consta
       // the four dot products of the pixel, summed over its LP lanes; the per-pixel algebra that turns them into
       // grad-flow / grad-mask runs once per row below (lane = pixel), not once per step on every lane
       const float r = reduce4<LP>(sa, sb, sc, se, lq);
-      if (act && (lq % (LP / 4)) == 0) reinterpret_cast<float*>(&s_sum[warp][pa])[lq / (LP / 4)] = r;
+      if (act && (lq % (LP / 4)) == 0) reinterpret_cast<float*>(DET ? reinterpret_cast<float4*>(&s_off[warp][pa]) : &s_sum[DET ? 0 : warp][pa])[lq / (LP / 4)] = r;
     }
     if (DO_GX) gxl += G * pxb;
     gol += G * pxb;
@@ -1271,7 +1275,7 @@ __global__ void __launch_bounds__(256, 4) gather_nhwc_kernel(const __grid_consta
   if (DO_GF) {
     __syncwarp();
     if (live) {
-      const float4 sum = s_sum[warp][lane];
+      const float4 sum = DET ? *reinterpret_cast<const float4*>(&s_off[warp][lane]) : s_sum[DET ? 0 : warp][lane];
       const float4 aux = s_aux[warp][lane];  // ax, ay, mask, flags
       const int ok = __float_as_int(aux.w);
       // corners outside the image contribute nothing (ATen within_bounds)
