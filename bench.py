@@ -321,7 +321,7 @@ def measure_traffic(args, kernel_regex):
                ["--frames", str(args.frames)] if args.frames else [])
     try:
         env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
-        r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=150, env=env)
     except (OSError, subprocess.TimeoutExpired) as e:
         return None, "ncu child failed: %s" % type(e).__name__
     total, seen = 0.0, 0
