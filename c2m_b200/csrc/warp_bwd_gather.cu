@@ -18,7 +18,7 @@
 //   gather_nchw_kernel one thread per pixel, channel loop, same two roles.
 //
 // Algorithmic bytes per pixel: read gout (C) + read x (C) + write gx (C) + flow/mask in, gflow/gmask
-// out.  Measured DRAM traffic of the channels-last pipeline: 1.05 x that (profiles/traffic.json); no
+// out.  Measured DRAM traffic of the channels-last pipeline: 1.02 - 1.05 x that (bench.py roofline.traffic); no
 // zero-fill, no read-modify-write of grad-input.
 #include <climits>
 #include <cstdlib>
