@@ -74,7 +74,9 @@ __global__ void __launch_bounds__(256) flowcon_fwd_kernel(const FcParams p, doub
   __shared__ double s_warp[8];
   const Dims& d = p.d;
   const int HW = d.H * d.W;
-  double acc = 0.0;
+  // per-thread sums in float (a thread sees a few dozen terms; the FP64 pipe of this part is 1/64 rate and the
+  // double additions were the kernel's bound), per-block and final sums in double in a fixed order
+  float acc = 0.f;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < p.total;
        idx += (int64_t)gridDim.x * blockDim.x) {
     const FcPixel q = fc_decode(p, idx, HW);
@@ -97,11 +99,12 @@ __global__ void __launch_bounds__(256) flowcon_fwd_kernel(const FcParams p, doub
       const float m = __ldg(p.mask_bw + q.o1);
       b = m * fabsf(w0 + bx) + m * fabsf(w1 + by);
     }
-    acc += (double)a + (double)b;
+    acc += a + b;
   }
+  double wacc = (double)acc;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = acc;
+  for (int o = 16; o > 0; o >>= 1) wacc += __shfl_xor_sync(0xffffffffu, wacc, o);
+  if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = wacc;
   __syncthreads();
   if (threadIdx.x == 0) {
     double s = 0.0;
@@ -138,8 +141,9 @@ __device__ __forceinline__ void fc_scatter(long long* acc, const FcPixel& q, int
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     if (!ok[k]) continue;
-    if (s0 != 0.f) atomicAdd(reinterpret_cast<unsigned long long*>(a0 + off[k]), (unsigned long long)__double2ll_rn((double)(s0 * w[k]) * kFcFix));
-    if (s1 != 0.f) atomicAdd(reinterpret_cast<unsigned long long*>(a1 + off[k]), (unsigned long long)__double2ll_rn((double)(s1 * w[k]) * kFcFix));
+    // (scaling a float by 2^32 is exact, so the conversion needs no double arithmetic -- the FP64 pipe is 1/64 rate)
+    if (s0 != 0.f) atomicAdd(reinterpret_cast<unsigned long long*>(a0 + off[k]), (unsigned long long)__float2ll_rn((s0 * w[k]) * 4294967296.f));
+    if (s1 != 0.f) atomicAdd(reinterpret_cast<unsigned long long*>(a1 + off[k]), (unsigned long long)__float2ll_rn((s1 * w[k]) * 4294967296.f));
   }
 }
 
