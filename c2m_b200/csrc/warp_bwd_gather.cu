@@ -1535,14 +1535,17 @@ static LocalWs carve_local(void* base, int64_t N, int H, int W, int64_t x_batch,
   o += up256(nov * npix_o * sizeof(int));
   w.pixrec = reinterpret_cast<int4*>(b + o);
   o += up256(npix_o * sizeof(int4));
-  w.bstart = reinterpret_cast<int*>(b + o);
-  o += up256(ntile * sizeof(int));
-  w.flex_list = reinterpret_cast<int*>(b + o);
-  o += up256(ntile * sizeof(int));
-  w.iseg_list = reinterpret_cast<int*>(b + o);
-  o += up256((size_t)N * H * ((W + 31) / 32) * sizeof(int));
-  w.pool = reinterpret_cast<int*>(b + o);
-  o += up256(4 * npix_o * sizeof(int));
+  w.bstart = w.flex_list = w.iseg_list = w.pool = nullptr;
+  if (det) {  // the counting sort of incoherent segments serves the deterministic mode only
+    w.bstart = reinterpret_cast<int*>(b + o);
+    o += up256(ntile * sizeof(int));
+    w.flex_list = reinterpret_cast<int*>(b + o);
+    o += up256(ntile * sizeof(int));
+    w.iseg_list = reinterpret_cast<int*>(b + o);
+    o += up256((size_t)N * H * ((W + 31) / 32) * sizeof(int));
+    w.pool = reinterpret_cast<int*>(b + o);
+    o += up256(4 * npix_o * sizeof(int));
+  }
   w.gpart = nullptr;
   w.slices = slices;
   if (small) {

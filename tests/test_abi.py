@@ -106,9 +106,10 @@ def test_workspace_size_contract():
             slices, c4 = slices * 2, c4 // 2
         nov = 1 + slices if slices > 1 else 1
         v = up(4 * (3 * ntile + 4)) + nov * up(npo) + up(8 * ntile * cap) + up(4 * nov * npo) + up(16 * npo)
-        # incoherent flows (counting sort of their pixels by destination tile): tile offsets, flex-tile list, the
-        # list of incoherent segments, and the pool of registered pixels (at most four tiles per pixel)
-        v += 2 * up(4 * ntile) + up(4 * N * H * ((W + 31) // 32)) + up(16 * npo)
+        if det:
+            # incoherent flows (counting sort of their pixels by destination tile, deterministic mode): tile offsets,
+            # heavy-tile list, the list of incoherent segments, the pool of registered pixels (<= four tiles per pixel)
+            v += 2 * up(4 * ntile) + up(4 * N * H * ((W + 31) // 32)) + up(16 * npo)
         if slices > 1:
             v += up(slices * 3 * npo * 4)
         if det:  # + scale bits, touched flags, per-destination corner counts, per-image incoherent-segment counters and the int64 overflow rows
