@@ -1,4 +1,5 @@
-"""Stand-in for src/losses/losses.py: the warp call sites (:115-141 FlowConsistLoss, :219-222 the warped term)."""
+"""Stand-in for src/losses/losses.py: binds `resample` from utils.ops at import time (:6) and uses it at the two
+loss-side call sites (flow consistency :115-141, warped-frame L1 :219-222), in this repo's own wording."""
 import torch
 import torch.nn.functional as F
 from torch import nn
@@ -6,31 +7,27 @@ from torch import nn
 from utils.ops import resample
 
 
+def _fold_frames(t):
+    return t.transpose(1, 2).transpose(0, 1).reshape(-1, t.shape[1], *t.shape[3:])
+
+
 class FlowConsistLoss(nn.Module):
     def __init__(self, train_params):
         super().__init__()
         self.train_params = train_params
 
-    @staticmethod
-    def _flowconsist(flow, flowback, mask_fw=None, mask_bw=None):
-        if mask_fw is not None:
-            nextloss = (mask_fw * torch.abs(resample(flowback, flow) + flow)).mean()
-            prevloss = (mask_bw * torch.abs(resample(flow, flowback) + flowback)).mean()
-        else:
-            nextloss = torch.abs(resample(flowback, flow) + flow).mean()
-            prevloss = torch.abs(resample(flow, flowback) + flowback).mean()
-        return prevloss + nextloss
-
     def forward(self, flow, flowback, mask_fw=None, mask_bw=None):
-        fold = lambda t: torch.cat(torch.unbind(t, dim=2), dim=0)  # noqa: E731
-        if mask_bw is not None:
-            v = self._flowconsist(fold(flow), fold(flowback), fold(mask_fw), fold(mask_bw))
-        else:
-            v = self._flowconsist(fold(flow), fold(flowback))
-        return v * self.train_params["num_predicted_frames"]
+        use_masks = mask_bw is not None
+        total = 0.0
+        for moving, field, mask in ((flowback, flow, mask_fw), (flow, flowback, mask_bw)):
+            field2 = _fold_frames(field)
+            err = (resample(_fold_frames(moving), field2) + field2).abs()
+            if use_masks:
+                err = _fold_frames(mask) * err
+            total = total + err.mean()
+        return total * self.train_params["num_predicted_frames"]
 
 
 def warped_term(source_frame, dense_motion_bw, target_frames):
-    T = dense_motion_bw.shape[2]
-    warped = torch.cat([resample(source_frame, dense_motion_bw[:, :, i]).unsqueeze(2) for i in range(T)], 2)
-    return F.l1_loss(warped, target_frames)
+    frames = [resample(source_frame, dense_motion_bw[:, :, t]) for t in range(dense_motion_bw.shape[2])]
+    return F.l1_loss(torch.stack(frames, 2), target_frames)

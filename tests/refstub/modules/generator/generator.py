@@ -1,9 +1,14 @@
-"""Stand-in for src/modules/generator/generator.py: binds `resample` at import time like the reference (:8) and keeps
-the two warp entry points on the class (:80-96)."""
+"""Stand-in for the import structure of src/modules/generator/generator.py: the module binds `resample` by value at
+import time (the reference does, :8) and the class carries the two warp entry points under the reference's names
+(:80-96).  Bodies are this repo's own wording of the oracle's composition; the network around them is a toy."""
 import torch.nn.functional as F
 from torch import nn
 
 from utils import resample
+
+
+def _to_size(t, size):
+    return t if tuple(t.shape[-2:]) == tuple(size) else F.interpolate(t, size=tuple(size), mode="bilinear")
 
 
 class OcclusionAwareGenerator(nn.Module):
@@ -14,21 +19,13 @@ class OcclusionAwareGenerator(nn.Module):
 
     @staticmethod
     def deform_input(inp, optical_flow):
-        _, h_old, w_old, _ = optical_flow.shape
-        _, _, h, w = inp.shape
-        if h_old != h or w_old != w:
-            optical_flow = F.interpolate(optical_flow, size=(h, w), mode="bilinear")
-        return resample(inp, optical_flow)
+        return resample(inp, _to_size(optical_flow, inp.shape[-2:]))
 
     def apply_optical(self, input_ref=None, optical_flow=None, occlusion_map=None):
-        out = self.deform_input(input_ref, optical_flow)
-        if occlusion_map is not None:
-            if out.shape[2] != occlusion_map.shape[2] or out.shape[3] != occlusion_map.shape[3]:
-                occlusion_map = F.interpolate(occlusion_map, size=out.shape[2:], mode="bilinear")
-            out = out * occlusion_map
-        return out
+        warped = self.deform_input(input_ref, optical_flow)
+        return warped if occlusion_map is None else warped * _to_size(occlusion_map, warped.shape[-2:])
 
     def forward(self, first_frame, flow, occlusion_map):
-        out = self.apply_optical(input_ref=self.enc(first_frame), optical_flow=flow, occlusion_map=occlusion_map)
-        image = self.apply_optical(input_ref=first_frame, optical_flow=flow)  # the C = 3, no-mask call site (:129-131)
-        return F.interpolate(self.dec(out), size=image.shape[2:], mode="bilinear") + image
+        deep = self.apply_optical(input_ref=self.enc(first_frame), optical_flow=flow, occlusion_map=occlusion_map)
+        image = self.apply_optical(input_ref=first_frame, optical_flow=flow)  # the C = 3 call site without a mask
+        return F.interpolate(self.dec(deep), size=image.shape[2:], mode="bilinear") + image
