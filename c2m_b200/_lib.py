@@ -67,7 +67,8 @@ RESIZE_CORNERS_RESCALE = 1   # utils.py:346-354: align_corners=True, flow values
 
 class Resize(ctypes.Structure):
     """struct c2m_resize of include/c2m_warp.h: the sizes the flow / mask are passed at (0 = the feature size)."""
-    _fields_ = [("flow_h", _int), ("flow_w", _int), ("mask_h", _int), ("mask_w", _int), ("flow_mode", _int)]
+    _fields_ = [("flow_h", _int), ("flow_w", _int), ("mask_h", _int), ("mask_w", _int), ("flow_mode", _int),
+                ("fold_t", _int)]
 
 
 class C2MWarpError(RuntimeError):
@@ -168,9 +169,9 @@ def strides4(s) -> "_Strides":
 
 
 @functools.lru_cache(maxsize=256)
-def resize_spec(flow_h, flow_w, mask_h, mask_w, flow_mode):
-    """ctypes c2m_resize (cached) or None when nothing is resized."""
-    return Resize(int(flow_h), int(flow_w), int(mask_h), int(mask_w), int(flow_mode))
+def resize_spec(flow_h, flow_w, mask_h, mask_w, flow_mode, fold_t=0):
+    """ctypes c2m_resize (cached)."""
+    return Resize(int(flow_h), int(flow_w), int(mask_h), int(mask_w), int(flow_mode), int(fold_t))
 
 
 def warp_blend_fwd(x_ptr, flow_ptr, mask_ptr, other_ptr, out_ptr, N, C, H, W, x_batch, x_strides, out_strides,
@@ -197,7 +198,8 @@ def _ws_bytes_cached(N, C, H, W, x_batch, want_gx, flags, rs_key):
 
 def bwd_workspace_bytes(N, C, H, W, x_batch, want_gx, flags, resize=None) -> int:
     """Workspace size of the backward (cached per argument tuple: the query is a pure function of its arguments)."""
-    key = None if resize is None else (resize.flow_h, resize.flow_w, resize.mask_h, resize.mask_w, resize.flow_mode)
+    key = None if resize is None else (resize.flow_h, resize.flow_w, resize.mask_h, resize.mask_w, resize.flow_mode,
+                                       resize.fold_t)
     return _ws_bytes_cached(int(N), int(C), int(H), int(W), int(x_batch), int(bool(want_gx)), int(flags), key)
 
 

@@ -287,7 +287,7 @@ size_t c2m_warp_bwd_workspace_bytes_rs(int64_t N, int C, int H, int W, int64_t x
   size_t b = bwd_workspace_bytes(N, C, H, W, x_batch, want_gx, flags);
   if (rs && N > 0 && H > 0 && W > 0) {
     const bool on = (rs->flow_h > 0 && rs->flow_h != H) || (rs->flow_w > 0 && rs->flow_w != W) ||
-                    (rs->mask_h > 0 && rs->mask_h != H) || (rs->mask_w > 0 && rs->mask_w != W);
+                    (rs->mask_h > 0 && rs->mask_h != H) || (rs->mask_w > 0 && rs->mask_w != W) || rs->fold_t > 0;
     if (on) b += resize_ws_bytes(N, H, W);
   }
   return b;

@@ -32,7 +32,17 @@ struct Resize {
   float fsy, fsx;  // flow: source-index scale (in-1)/(out-1) or in/out, float32 as ATen forms it
   float msy, msx;  // mask: in/out
   float fmulx, fmuly;  // flow value rescale: 1/(old/new) as a float32 reciprocal (ATen CUDA div-by-scalar), else 1
+  int fold_t, fold_b;  // > 0: flow / mask are 5-D clips [B,c,T,h,w]; frame n = t * B + b reads plane (b, :, t)
 };
+
+// element offset of plane (frame n, channel c) of a [N,nc,h,w] tensor -- or of the 5-D clip [B,nc,T,h,w] it is a fold of
+__device__ __forceinline__ int64_t plane_offset(const Resize& rs, int n, int c, int nc, int64_t hw) {
+  if (rs.fold_t > 0) {
+    const int t = n / rs.fold_b, b = n - t * rs.fold_b;
+    return (((int64_t)b * nc + c) * rs.fold_t + t) * hw;
+  }
+  return ((int64_t)n * nc + c) * hw;
+}
 
 struct Dims {
   int N, C, H, W;
@@ -143,9 +153,16 @@ __device__ __forceinline__ void fetch_flow_mask(const Dims& d, const float* __re
                                                 float& m) {
   const Resize& rs = d.rs;
   if (rs.on & 1) {
-    const float* f0 = flow + (int64_t)n * 2 * rs.fh * rs.fw;
-    fx = bilerp_plane(f0, rs.fh, rs.fw, rs.fsy, rs.fsx, rs.f_align != 0, i, j);
-    fy = bilerp_plane(f0 + (int64_t)rs.fh * rs.fw, rs.fh, rs.fw, rs.fsy, rs.fsx, rs.f_align != 0, i, j);
+    const int64_t fhw = (int64_t)rs.fh * rs.fw;
+    const float* f0 = flow + plane_offset(rs, n, 0, 2, fhw);
+    const float* f1 = flow + plane_offset(rs, n, 1, 2, fhw);
+    if (rs.fh == d.H && rs.fw == d.W) {  // folded clip at the feature size: a plain read (ATen copies in that case)
+      fx = __ldg(f0 + i * d.W + j);
+      fy = __ldg(f1 + i * d.W + j);
+    } else {
+      fx = bilerp_plane(f0, rs.fh, rs.fw, rs.fsy, rs.fsx, rs.f_align != 0, i, j);
+      fy = bilerp_plane(f1, rs.fh, rs.fw, rs.fsy, rs.fsx, rs.f_align != 0, i, j);
+    }
     if (rs.f_align) {
       fx = __fmul_rn(fx, rs.fmulx);
       fy = __fmul_rn(fy, rs.fmuly);
@@ -156,10 +173,13 @@ __device__ __forceinline__ void fetch_flow_mask(const Dims& d, const float* __re
     fy = __ldg(fl + d.H * d.W);
   }
   if (mask) {
-    if (rs.on & 2)
-      m = bilerp_plane(mask + (int64_t)n * rs.mh * rs.mw, rs.mh, rs.mw, rs.msy, rs.msx, false, i, j);
-    else
+    if (rs.on & 2) {
+      const float* m0 = mask + plane_offset(rs, n, 0, 1, (int64_t)rs.mh * rs.mw);
+      m = (rs.mh == d.H && rs.mw == d.W) ? __ldg(m0 + i * d.W + j)
+                                         : bilerp_plane(m0, rs.mh, rs.mw, rs.msy, rs.msx, false, i, j);
+    } else {
       m = __ldg(mask + (int64_t)n * d.H * d.W + i * d.W + j);
+    }
   } else {
     m = 1.f;
   }

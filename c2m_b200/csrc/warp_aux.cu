@@ -40,6 +40,15 @@ int fill_resize(Dims& d, const c2m_resize* rs) {
   // needs work here
   if (fh != d.H || fw != d.W) r.on |= 1;
   if (mh != d.H || mw != d.W) r.on |= 2;
+  if (rs->fold_t < 0 || (rs->fold_t > 0 && d.N % rs->fold_t != 0)) {
+    set_error("fold_t=%d must divide N=%d", rs->fold_t, d.N);
+    return C2M_ERR_INVALID;
+  }
+  if (rs->fold_t > 0) {  // 5-D clips: every plane is addressed through the fold, resized or not
+    r.fold_t = rs->fold_t;
+    r.fold_b = d.N / rs->fold_t;
+    r.on |= 3;
+  }
   // ATen area_pixel_compute_scale<float>: align_corners ? (in-1)/(out-1) (0 when out == 1) : in/out
   if (r.f_align) {
     r.fsy = d.H > 1 ? (float)(fh - 1) / (float)(d.H - 1) : 0.f;
@@ -148,11 +157,10 @@ __global__ void __launch_bounds__(256) resize_bwd_kernel(const Dims d, const flo
       }
     }
     if (is_flow) {
-      float* o = gflow_src + (int64_t)n * 2 * Hs * Ws + r;
-      o[0] = a0 * rs.fmulx;
-      o[(int64_t)Hs * Ws] = a1 * rs.fmuly;
+      gflow_src[plane_offset(rs, n, 0, 2, (int64_t)Hs * Ws) + r] = a0 * rs.fmulx;
+      gflow_src[plane_offset(rs, n, 1, 2, (int64_t)Hs * Ws) + r] = a1 * rs.fmuly;
     } else {
-      gmask_src[k] = a0;
+      gmask_src[plane_offset(rs, n, 0, 1, (int64_t)Hs * Ws) + r] = a0;
     }
   }
 }

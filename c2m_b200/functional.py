@@ -78,10 +78,12 @@ def _workspace(nbytes: int, device: torch.device, stream) -> torch.Tensor:
 
 
 def _resize_spec(x, flow, mask, flow_resize):
-    """c2m_resize for a flow / mask held at another resolution than x (None: same size)."""
+    """c2m_resize for a flow / mask held at another resolution than x, or as 5-D clips (None: plain [N,c,H,W])."""
     H, W = x.shape[2:]
-    fh, fw = flow.shape[2:]
-    mh, mw = (mask.shape[2:] if mask is not None else (H, W))
+    fh, fw = flow.shape[-2:]
+    mh, mw = (mask.shape[-2:] if mask is not None else (H, W))
+    if flow.dim() == 5:  # [B,2,T,h,w] (+ mask [B,1,T,h',w']): frame n = t * B + b, no folded copies
+        return _lib.resize_spec(fh, fw, mh, mw, _RESIZE_MODES[flow_resize or "half_pixel"], flow.shape[2])
     if (fh, fw) == (H, W) and (mh, mw) == (H, W):
         return None
     if (fh, fw) != (H, W) and flow_resize is None:
@@ -102,21 +104,28 @@ def _check_inputs(x, flow, mask, other, resized=False):
             raise TypeError(f"c2m_b200.warp_blend: `{name}` must be float32, got {t.dtype}")
         if t.device != x.device:
             raise RuntimeError("c2m_b200.warp_blend: all tensors must be on the same device")
-    if x.dim() != 4 or flow.dim() != 4 or flow.shape[1] != 2:
+    if x.dim() != 4 or flow.dim() not in (4, 5) or flow.shape[1] != 2:
         raise ValueError(f"expected x [B,C,H,W] and flow [N,2,H,W], got {tuple(x.shape)} and {tuple(flow.shape)}")
-    N = flow.shape[0]
+    if flow.dim() == 5:  # 5-D clips [B',2,T,h,w] / [B',1,T,h',w']
+        N = flow.shape[0] * flow.shape[2]
+        if mask is not None and (mask.dim() != 5 or mask.shape[:3] != (flow.shape[0], 1, flow.shape[2])):
+            raise ValueError(f"a 5-D flow {tuple(flow.shape)} needs a 5-D mask [B,1,T,h,w], got {tuple(mask.shape)}")
+        if other is not None:
+            raise ValueError("`other` is not supported together with 5-D clips")
+    else:
+        N = flow.shape[0]
+        if mask is not None and (mask.dim() != 4 or mask.shape[0] != N or mask.shape[1] != 1):
+            raise ValueError(f"mask must be [N,1,h,w] with N={N}, got {tuple(mask.shape)}")
     H, W = x.shape[2:]
     B = x.shape[0]
     if B != N and (B == 0 or N % B != 0):
         raise ValueError(f"x batch {B} must equal or divide the flow batch {N}")
-    if mask is not None and (mask.dim() != 4 or mask.shape[0] != N or mask.shape[1] != 1):
-        raise ValueError(f"mask must be [N,1,h,w] with N={N}, got {tuple(mask.shape)}")
     if not resized:
         if tuple(flow.shape[2:]) != (H, W):
             raise ValueError(f"flow {tuple(flow.shape)} does not match x {tuple(x.shape)} spatially")
         if mask is not None and tuple(mask.shape) != (N, 1, H, W):
             raise ValueError(f"mask must be [N,1,H,W]={N, 1, H, W}, got {tuple(mask.shape)}")
-    elif min(flow.shape[2:]) == 0 or (mask is not None and min(mask.shape[2:]) == 0):
+    elif min(flow.shape[-2:]) == 0 or (mask is not None and min(mask.shape[-2:]) == 0):
         raise ValueError("cannot resize an empty flow / mask")
     if other is not None:
         if mask is None:
@@ -133,7 +142,7 @@ class WarpBlendFunction(torch.autograd.Function):
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(ctx, x, flow, mask, other, padding, deterministic, flags, flow_resize=None):
-        if x.dim() != 4 or flow.dim() != 4:
+        if x.dim() != 4 or flow.dim() not in (4, 5):
             raise ValueError(f"expected x [B,C,H,W] and flow [N,2,h,w], got {tuple(x.shape)} and {tuple(flow.shape)}")
         rs = _resize_spec(x, flow, mask, flow_resize)
         _check_inputs(x, flow, mask, other, resized=rs is not None)
@@ -142,7 +151,7 @@ class WarpBlendFunction(torch.autograd.Function):
         flow = flow.contiguous()
         mask = None if mask is None else mask.contiguous()
         other = None if other is None else _dense(other, nhwc)
-        N = flow.shape[0]
+        N = flow.shape[0] * (flow.shape[2] if flow.dim() == 5 else 1)
         H, W = x.shape[2:]
         B, C = x.shape[0], x.shape[1]
         out = torch.empty((N, C, H, W), dtype=x.dtype, device=x.device,
@@ -165,7 +174,7 @@ class WarpBlendFunction(torch.autograd.Function):
         need_mask = need_mask and mask is not None
         need_other = need_other and other is not None
         gout = _dense(gout, nhwc)
-        N = flow.shape[0]
+        N = flow.shape[0] * (flow.shape[2] if flow.dim() == 5 else 1)
         H, W = x.shape[2:]
         B, C = x.shape[0], x.shape[1]
         gx = torch.empty_like(x) if need_x else None
@@ -203,6 +212,9 @@ def warp_blend(x, flow, mask=None, other=None, padding="border", deterministic=N
            the kernel (bilinear; the gradients come back at their own sizes): "half_pixel" = generator.py:84-85
            (align_corners=False, values kept), "corners_rescaled" = utils.py:346-354 (align_corners=True, values
            scaled by new/old).  The mask is always resized with align_corners=False (generator.py:92).
+           flow / mask may also be the reference's 5-D clips [B',2,T,h,w] / [B',1,T,h',w']: frame n = t * B' + b reads
+           plane (b, :, t) -- the fold torch.cat(torch.unbind(., 2), 0) of motion_autoencoder.py:120-123 without the
+           copies -- and their gradients come back 5-D.
     """
     if deterministic is None:
         deterministic = deterministic_default()

@@ -50,12 +50,12 @@ def decoder_warp(app_features: torch.Tensor, sparse_motion: torch.Tensor, sparse
     """One scale of DenseMotionDecoder.forward (motion_autoencoder.py:117-125).  The reference
     materialises T copies of the appearance map folded into the batch (t-major) before warping, resizes the
     motion with `resize_flow` (align_corners=True, values rescaled) and the occlusion with F.interpolate; here the
-    kernel reads image n % B and resizes both on the fly, so the features are read, and their gradient is
-    accumulated, in place.  sparse_motion [B,2,T,H,W], sparse_occlusion [B,1,T,H,W]."""
-    motion = torch.cat(torch.unbind(sparse_motion, 2), 0)
-    occ = torch.cat(torch.unbind(sparse_occlusion, 2), 0)
-    assert motion.shape[0] == app_features.shape[0] * num_frames
-    return warp_blend(app_features, motion, occ, flow_resize="corners_rescaled")
+    kernel reads image n % B, addresses the 5-D motion / occlusion clips through the fold (no torch.cat copies) and
+    resizes both on the fly, so the features are read, and their gradient is accumulated, in place.
+    sparse_motion [B,2,T,H,W], sparse_occlusion [B,1,T,H,W]."""
+    assert sparse_motion.shape[0] == app_features.shape[0] and sparse_motion.shape[2] == num_frames
+    # the 5-D clips go to the kernel as they are: frame n = t * B + b reads plane (b, :, t)
+    return warp_blend(app_features, sparse_motion, sparse_occlusion, flow_resize="corners_rescaled")
 
 
 _PATCH_TARGETS = (

@@ -125,6 +125,10 @@ typedef struct c2m_resize {
   int flow_h, flow_w; /* size of `flow` as passed; 0 = H, W */
   int mask_h, mask_w; /* size of `mask` as passed; 0 = H, W */
   int flow_mode;      /* C2M_RESIZE_* (ignored when the flow is not resized) */
+  int fold_t;         /* 0: flow [N,2,h,w], mask [N,1,h,w].  T > 0: the tensors are the reference's 5-D clips, flow
+                         [B,2,T,h,w] and mask [B,1,T,h,w] with B = N / T, and frame n = t * B + b reads plane (b, :, t)
+                         -- the fold `torch.cat(torch.unbind(., 2), 0)` of motion_autoencoder.py:120-123 without the
+                         copies; gflow / gmask are written in the same 5-D layout */
 } c2m_resize;
 
 C2M_API int c2m_warp_blend_fwd_rs(const float* x, const float* flow, const float* mask, const float* other,

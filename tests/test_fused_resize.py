@@ -162,3 +162,33 @@ def test_blend_operand_fast_kernels(dev, shape, layout):
     out = c2m_b200.warp_blend(x1, f1, m1, o1)
     gm, go = torch.autograd.grad(out, [m1, o1], gout)
     assert rel(gm, g2[2]) <= GRAD_TOL and rel(go, g2[3]) <= GRAD_TOL
+
+
+@pytest.mark.parametrize("same_size", [False, True])
+def test_five_d_clips_equal_the_folded_tensors(dev, same_size):
+    """warp_blend on the reference's 5-D clips [B,2,T,h,w] / [B,1,T,h,w] (frame n = t * B + b, no torch.cat copies)
+    gives the same bits as on the folded [T*B,...] tensors, and the gradients come back 5-D."""
+    B, T, C, H, W = 3, 4, 8, 12, 20
+    hs, ws = (H, W) if same_size else (24, 40)
+    g = torch.Generator().manual_seed(5 + same_size)
+    x = torch.randn(B, C, H, W, generator=g).to(dev)
+    motion = (torch.randn(B, 2, T, hs, ws, generator=g) * 3).to(dev)
+    occ = torch.rand(B, 1, T, hs, ws, generator=g).to(dev)
+    gout = torch.randn(B * T, C, H, W, generator=g).to(dev)
+    for mode in ("corners_rescaled", "half_pixel"):
+        x1, m1, o1 = leaves(x, motion, occ)
+        out5 = c2m_b200.warp_blend(x1, m1, o1, flow_resize=mode)
+        g5 = torch.autograd.grad(out5, [x1, m1, o1], gout)
+        x2, m2, o2 = leaves(x, motion, occ)
+        fold = lambda t: torch.cat(torch.unbind(t, 2), 0)  # noqa: E731
+        out4 = c2m_b200.warp_blend(x2, fold(m2), fold(o2), flow_resize=mode)
+        g4 = torch.autograd.grad(out4, [x2, m2, o2], gout)
+        assert torch.equal(out5, out4)
+        assert g5[1].shape == motion.shape and g5[2].shape == occ.shape
+        for a, b in zip(g5, g4):
+            assert rel(a, b) <= 1e-6
+    # no mask, forward only
+    assert torch.equal(c2m_b200.warp_blend(x, motion, None, flow_resize="half_pixel"),
+                       c2m_b200.warp_blend(x, torch.cat(torch.unbind(motion, 2), 0), None, flow_resize="half_pixel"))
+    with pytest.raises(ValueError):
+        c2m_b200.warp_blend(x, motion, occ[:, :, 0], flow_resize="half_pixel")
