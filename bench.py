@@ -385,6 +385,14 @@ def run_ours(args):
     det = bool(args.deterministic)
     flags = int(args.flags, 0)
     peak, peak_src = measured_peak()
+    if not nhwc:
+        # the upstream gradient arrives in the format of the result it belongs to (an NCHW x gives channels-last
+        # strided results unless the strict policy is on: c2m_b200/functional.py)
+        with torch.no_grad():
+            o_probe = c2m_b200.warp_blend(x.detach(), flow.detach(), mask.detach(), deterministic=det, flags=flags)
+        if not o_probe.is_contiguous():
+            gout = gout.contiguous(memory_format=torch.channels_last)
+        del o_probe
 
     def step(ev=None):
         if ev:
@@ -434,15 +442,31 @@ def run_ours(args):
                 x2 = x.detach().contiguous(memory_format=torch.channels_last).requires_grad_(True)
                 g2 = gout.contiguous(memory_format=torch.channels_last)
 
-            def step2():
-                o = c2m_b200.warp_blend(x2, flow, mask, deterministic=det, flags=flags)
-                torch.autograd.grad(o, [x2, flow, mask], g2)
+            def time_other(flags2, g):
+                def step2():
+                    o = c2m_b200.warp_blend(x2, flow, mask, deterministic=det, flags=flags | flags2)
+                    torch.autograd.grad(o, [x2, flow, mask], g)
 
-            oms, ot0, ot1 = _time_steps(step2, 5, 3, barrier)
-            oach = (fwd_bytes(N, C, H, W) + bwd_bytes(N, C, H, W)) / (oms * 1e-3) / 1e9
-            other = {"layout": "nchw" if nhwc else "nhwc", "ms_per_step": oms,
-                     "frames_per_s_per_gpu": N / (oms * 1e-3), "achieved": oach, "frac": oach / peak,
-                     "clocks": clk.window(ot0, ot1)}
+                oms, ot0, ot1 = _time_steps(step2, 5, 3, barrier)
+                oach = (fwd_bytes(N, C, H, W) + bwd_bytes(N, C, H, W)) / (oms * 1e-3) / 1e9
+                return {"ms_per_step": oms, "frames_per_s_per_gpu": N / (oms * 1e-3), "achieved": oach,
+                        "frac": oach / peak, "clocks": clk.window(ot0, ot1)}
+
+            if nhwc:
+                # NCHW-contiguous x, the reference's layout.  Default policy: x is converted once in the forward and
+                # the results come back channels-last strided, so the upstream gradient arrives in that format too
+                # (what a consumer of a channels_last tensor hands back); "strict": results keep x's strides, the
+                # upstream gradient is NCHW, the backward stages three tensors through channels-last copies
+                with torch.no_grad():
+                    o_probe = c2m_b200.warp_blend(x2, flow, mask, deterministic=det, flags=flags)
+                g_like = g2 if o_probe.is_contiguous() else gout
+                del o_probe
+                other = {"layout": "nchw", "policy": "x converted once in the forward, channels-last results",
+                         **time_other(0, g_like)}
+                other["gout_nchw"] = time_other(0, g2)
+                other["strict"] = time_other(_lib.FLAG_STRICT_LAYOUT, g2)
+            else:
+                other = {"layout": "nhwc", **time_other(0, g2)}
             del x2, g2
 
         # ---- secondary figures: the multi-scale sites of the reference, N frames each, all levels

@@ -26,6 +26,8 @@ FLAG_NO_TMA = 0x800
 FLAG_BWD_ATOMIC = 0x1000
 FLAG_STAGE_NHWC = 0x4000
 FLAG_NO_STAGE = 0x8000  # host-side only: keep NCHW tensors on the NCHW kernels (test / tuning hook)
+FLAG_PLANNED = 0x20000  # bwd: the workspace is a plan made by c2m_warp_plan in the forward call
+FLAG_STRICT_LAYOUT = 0x10000  # host-side only: results keep x's strides (NCHW x: staged backward, no promotion)
 
 # every symbol include/c2m_warp.h declares (tests/test_abi.py checks the list against the header)
 SYMBOLS = (
@@ -38,6 +40,10 @@ SYMBOLS = (
     "c2m_warp_blend_bwd_rs",
     "c2m_warp_bwd_workspace_bytes_rs",
     "c2m_base_grid",
+    "c2m_relayout",
+    "c2m_warp_plan_bytes",
+    "c2m_warp_plan",
+    "c2m_warp_blend_fwd_plan",
     "c2m_warp_launch_count",
     "c2m_occlusion_map",
     "c2m_occlusion_map_workspace_bytes",
@@ -121,6 +127,16 @@ def load(build_if_missing: bool = False) -> ctypes.CDLL:
         lib.c2m_warp_bwd_workspace_bytes_rs.argtypes = [_i64, _int, _int, _int, _i64, _int, ctypes.POINTER(Resize), _int]
         lib.c2m_base_grid.restype = _int
         lib.c2m_base_grid.argtypes = [_ptr, _i64, _int, _int, _ptr]
+        lib.c2m_warp_plan_bytes.restype = ctypes.c_size_t
+        lib.c2m_warp_plan_bytes.argtypes = [_i64, _int, _int, _int, _i64, _int]
+        lib.c2m_warp_plan.restype = _int
+        lib.c2m_warp_plan.argtypes = [_ptr, _ptr, _i64, _int, _int, _int, _i64, _int, _int, _ptr, ctypes.c_size_t, _ptr]
+        lib.c2m_warp_blend_fwd_plan.restype = _int
+        lib.c2m_warp_blend_fwd_plan.argtypes = [_ptr, _ptr, _ptr, _ptr, _ptr, _i64, _int, _int, _int, _i64,
+                                                ctypes.POINTER(_i64), ctypes.POINTER(_i64), _int, _int, _ptr,
+                                                ctypes.c_size_t, _ptr]
+        lib.c2m_relayout.restype = _int
+        lib.c2m_relayout.argtypes = [_ptr, _ptr, _i64, _int, _int, _int, _int, _ptr]
         lib.c2m_warp_profile.restype = _int
         lib.c2m_warp_profile.argtypes = [_int]
         lib.c2m_warp_profile_last_ms.restype = ctypes.c_float
@@ -181,6 +197,14 @@ def warp_blend_fwd(x_ptr, flow_ptr, mask_ptr, other_ptr, out_ptr, N, C, H, W, x_
     _check(rc, "c2m_warp_blend_fwd")
 
 
+def warp_blend_fwd_plan(x_ptr, flow_ptr, mask_ptr, other_ptr, out_ptr, N, C, H, W, x_batch, x_strides, out_strides,
+                        padding, flags, plan_ptr, plan_nbytes, stream) -> None:
+    rc = load().c2m_warp_blend_fwd_plan(x_ptr, flow_ptr, mask_ptr, other_ptr, out_ptr, N, C, H, W, x_batch,
+                                        strides4(x_strides), strides4(out_strides), padding, flags, plan_ptr,
+                                        plan_nbytes, stream)
+    _check(rc, "c2m_warp_blend_fwd_plan")
+
+
 def warp_blend_bwd(x_ptr, flow_ptr, mask_ptr, other_ptr, gout_ptr, gx_ptr, gflow_ptr, gmask_ptr, gother_ptr,
                    N, C, H, W, x_batch, x_strides, g_strides, padding, flags, ws_ptr, ws_bytes, stream,
                    resize=None) -> None:
@@ -205,6 +229,20 @@ def bwd_workspace_bytes(N, C, H, W, x_batch, want_gx, flags, resize=None) -> int
 
 def base_grid(grid_ptr, N, H, W, stream) -> None:
     _check(load().c2m_base_grid(grid_ptr, N, H, W, stream), "c2m_base_grid")
+
+
+@functools.lru_cache(maxsize=1024)
+def plan_bytes(N, C, H, W, x_batch, flags) -> int:
+    return int(load().c2m_warp_plan_bytes(N, C, H, W, x_batch, flags))
+
+
+def warp_plan(flow_ptr, mask_ptr, N, C, H, W, x_batch, padding, flags, plan_ptr, nbytes, stream) -> None:
+    _check(load().c2m_warp_plan(flow_ptr, mask_ptr, N, C, H, W, x_batch, padding, flags, plan_ptr, nbytes, stream),
+           "c2m_warp_plan")
+
+
+def relayout(src_ptr, dst_ptr, N, C, H, W, to_channels_last, stream) -> None:
+    _check(load().c2m_relayout(src_ptr, dst_ptr, N, C, H, W, int(bool(to_channels_last)), stream), "c2m_relayout")
 
 
 OCC_COORDS = 0x1

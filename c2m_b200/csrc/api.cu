@@ -240,10 +240,10 @@ float c2m_warp_profile_last_ms(void) {
 
 static size_t up256(size_t v) { return (v + 255) & ~(size_t)255; }
 
-int c2m_warp_blend_fwd_rs(const float* x, const float* flow, const float* mask, const float* other, float* out,
-                          int64_t N, int C, int H, int W, int64_t x_batch, const int64_t x_strides[4],
-                          const int64_t out_strides[4], const c2m_resize* rs, int padding, int flags,
-                          void* cuda_stream) {
+static int fwd_entry(const float* x, const float* flow, const float* mask, const float* other, float* out,
+                     int64_t N, int C, int H, int W, int64_t x_batch, const int64_t x_strides[4],
+                     const int64_t out_strides[4], const c2m_resize* rs, int padding, int flags, void* plan,
+                     size_t plan_bytes_, void* cuda_stream) {
   FwdParams p;
   memset(&p, 0, sizeof(p));
   int rc = fill_dims(p.d, N, C, H, W, x_batch, padding, flags);
@@ -263,9 +263,51 @@ int c2m_warp_blend_fwd_rs(const float* x, const float* flow, const float* mask, 
   canonical(p.os, out_strides, lo, C, H, W);
   p.x = x; p.flow = flow; p.mask = mask; p.other = other; p.out = out;
   p.cchunk = C;
-  rc = launch_fwd(p, lx, lo, reinterpret_cast<cudaStream_t>(cuda_stream));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
+  bool plan_after = false;
+  if (plan) {
+    if (p.d.rs.on) {
+      set_error("c2m_warp_blend_fwd_plan: a resized flow / mask has no plan");
+      return C2M_ERR_INVALID;
+    }
+    if (fwd_makes_plan(p, lx, lo)) {  // the forward kernel registers its row segments itself
+      if ((rc = plan_bind(p.d, plan, plan_bytes_, p.plan, st)) != C2M_OK) return rc;
+    } else {
+      plan_after = true;  // another forward kernel runs: the plan is made by segbin_kernel right after it
+    }
+  }
+  rc = launch_fwd(p, lx, lo, st);
   if (rc) return rc;
+  if (plan_after) {
+    BwdParams b;
+    memset(&b, 0, sizeof(b));
+    b.d = p.d;
+    b.flow = flow;
+    b.mask = mask;
+    b.cchunk = C;
+    if ((rc = launch_plan(b, plan, plan_bytes_, st)) != C2M_OK) return rc;
+  }
   return check_launch("c2m_warp_blend_fwd");
+}
+
+int c2m_warp_blend_fwd_rs(const float* x, const float* flow, const float* mask, const float* other, float* out,
+                          int64_t N, int C, int H, int W, int64_t x_batch, const int64_t x_strides[4],
+                          const int64_t out_strides[4], const c2m_resize* rs, int padding, int flags,
+                          void* cuda_stream) {
+  return fwd_entry(x, flow, mask, other, out, N, C, H, W, x_batch, x_strides, out_strides, rs, padding, flags, nullptr,
+                   0, cuda_stream);
+}
+
+int c2m_warp_blend_fwd_plan(const float* x, const float* flow, const float* mask, const float* other, float* out,
+                            int64_t N, int C, int H, int W, int64_t x_batch, const int64_t x_strides[4],
+                            const int64_t out_strides[4], int padding, int flags, void* plan, size_t plan_bytes_,
+                            void* cuda_stream) {
+  if (!plan) {
+    set_error("c2m_warp_blend_fwd_plan: null plan buffer");
+    return C2M_ERR_INVALID;
+  }
+  return fwd_entry(x, flow, mask, other, out, N, C, H, W, x_batch, x_strides, out_strides, nullptr, padding, flags, plan,
+                   plan_bytes_, cuda_stream);
 }
 
 int c2m_warp_blend_fwd(const float* x, const float* flow, const float* mask, const float* other, float* out,
@@ -342,6 +384,10 @@ int c2m_warp_blend_bwd_rs(const float* x, const float* flow, const float* mask, 
   p.x = x; p.flow = flow; p.mask = mask; p.other = other; p.gout = gout;
   p.gx = gx; p.gflow = gflow; p.gmask = gmask; p.gother = gother;
   p.cchunk = C;
+  if (rsz.on && (flags & C2M_FLAG_PLANNED)) {
+    set_error("C2M_FLAG_PLANNED cannot be combined with a resized flow / mask");
+    return C2M_ERR_INVALID;
+  }
   if (rsz.on) {
     // the resized flow / mask are materialised once (the forward computes them on the fly), the kernels below run on
     // them unchanged, and the gradients go back through the resize in one gather pass
@@ -379,6 +425,51 @@ int c2m_warp_blend_bwd(const float* x, const float* flow, const float* mask, con
                        int flags, void* workspace, size_t workspace_bytes, void* cuda_stream) {
   return c2m_warp_blend_bwd_rs(x, flow, mask, other, gout, gx, gflow, gmask, gother, N, C, H, W, x_batch, x_strides,
                                g_strides, nullptr, padding, flags, workspace, workspace_bytes, cuda_stream);
+}
+
+size_t c2m_warp_plan_bytes(int64_t N, int C, int H, int W, int64_t x_batch, int flags) {
+  Dims d;
+  memset(&d, 0, sizeof(d));
+  if (N <= 0 || C <= 0 || H <= 0 || W <= 0 || N > 0x7fffffff) return 0;
+  if (x_batch <= 0) x_batch = N;
+  if (x_batch > N || N % x_batch != 0) return 0;
+  d.N = (int)N; d.C = C; d.H = H; d.W = W; d.x_batch = (int)x_batch; d.flags = flags;
+  return plan_bytes(d);
+}
+
+int c2m_warp_plan(const float* flow, const float* mask, int64_t N, int C, int H, int W, int64_t x_batch, int padding,
+                  int flags, void* plan, size_t plan_bytes_, void* cuda_stream) {
+  BwdParams p;
+  memset(&p, 0, sizeof(p));
+  const int rc = fill_dims(p.d, N, C, H, W, x_batch, padding, flags);
+  if (rc) return rc;
+  if (!flow) {
+    set_error("null pointer argument");
+    return C2M_ERR_INVALID;
+  }
+  p.flow = flow;
+  p.mask = mask;
+  p.cchunk = C;
+  const int64_t nhwc[4] = {(int64_t)C * H * W, 1, (int64_t)W * C, C};
+  for (int k = 0; k < 4; ++k) p.xs[k] = p.gs[k] = nhwc[k];
+  const int r2 = launch_plan(p, plan, plan_bytes_, reinterpret_cast<cudaStream_t>(cuda_stream));
+  if (r2) return r2;
+  return check_launch("c2m_warp_plan");
+}
+
+int c2m_relayout(const float* src, float* dst, int64_t N, int C, int H, int W, int to_channels_last,
+                 void* cuda_stream) {
+  if (N < 0 || C < 0 || H < 0 || W < 0 || N > 65535 || (int64_t)H * W > 0x7fffffff) {
+    set_error("c2m_relayout: invalid sizes");
+    return C2M_ERR_INVALID;
+  }
+  if (N == 0 || C == 0 || H == 0 || W == 0) return C2M_OK;
+  if (!src || !dst) {
+    set_error("null pointer argument");
+    return C2M_ERR_INVALID;
+  }
+  launch_relayout(src, dst, N, C, H * W, to_channels_last != 0, reinterpret_cast<cudaStream_t>(cuda_stream));
+  return check_launch("c2m_relayout");
 }
 
 int c2m_base_grid(float* grid, int64_t N, int H, int W, void* cuda_stream) {

@@ -251,6 +251,12 @@ static void launch_transpose(const float* in, float* out, int64_t n, int C, int 
   count_launch();
 }
 
+// C-ABI relayout entry (c2m_relayout): the same staging copy on caller-owned tensors
+void launch_relayout(const float* in, float* out, int64_t n, int C, int HW, bool to_nhwc, cudaStream_t st) {
+  if (to_nhwc) launch_transpose<true>(in, out, n, C, HW, st);
+  else launch_transpose<false>(in, out, n, C, HW, st);
+}
+
 static int grid_for(int64_t total) {
   int64_t blocks = (total + 255) / 256;
   const int64_t cap = (int64_t)sm_count() * 32;
@@ -316,6 +322,11 @@ int launch_bwd(const BwdParams& pin, Layout lx, Layout lg, void* workspace, size
     q.x = q.gout = reinterpret_cast<const float*>(workspace);
     q.gx = reinterpret_cast<float*>(workspace);
     if (gather_supported(q, LAYOUT_NHWC, LAYOUT_NHWC)) return launch_bwd_staged(pin, workspace, workspace_bytes, st);
+  }
+  if ((pin.d.flags & C2M_FLAG_PLANNED) &&
+      !(lx == LAYOUT_NHWC && pin.gx && !(pin.d.flags & C2M_FLAG_DETERMINISTIC) && gather_supported(pin, lx, lg))) {
+    set_error("C2M_FLAG_PLANNED: this call does not take the channels-last float gather the plan was made for");
+    return C2M_ERR_INVALID;
   }
   if (gather_supported(pin, lx, lg))
     return launch_bwd_gather(pin, lx, reinterpret_cast<char*>(workspace) + 256,

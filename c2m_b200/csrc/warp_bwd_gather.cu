@@ -1732,6 +1732,92 @@ __global__ void __launch_bounds__(256) absmax_flat_kernel(const float* __restric
 
 __global__ void set_bits_kernel(unsigned* p, unsigned v) { *p = v; }
 
+// ---------------------------------------------------------------------------------------------
+// Plan (c2m_warp_plan): the segment registration of the channels-last float backward depends on the flow and the mask
+// only, so the forward call can run it -- on a second stream, next to the HBM-bound forward kernel (segbin_kernel is
+// bound by integer instructions: 0.07 ms of the headline backward that then cost nothing) -- into the buffer the
+// backward later receives as its workspace with C2M_FLAG_PLANNED.
+static void bind_local(BwdParams& p, const LocalWs& w) {
+  p.tcnt = w.tcnt;
+  p.bcount = w.bcount; p.bstart = w.bstart; p.bfill = w.bfill; p.pool = w.pool;
+  p.iseg_count = w.iseg_count; p.iseg_list = w.iseg_list;
+  p.flex_count = w.flex_count; p.flex_list = w.flex_list; p.flex_next = w.flex_next;
+  p.tlist = w.tlist;
+  p.cand_cap = w.cand_cap;
+  p.pixrec = w.pixrec;
+  p.gpart = w.gpart;
+  p.ovf_stride = (int64_t)w.ovf_stride;
+  p.cchunk = p.d.C / w.slices;  // small pyramid level: every pass of this call uses the same channel slicing
+  p.ovf = w.ovf;
+  p.ovf_count = w.ovf_count;
+  p.ovf_list = w.ovf_list;
+}
+
+static bool plan_supported(const Dims& d) {
+  if (d.flags & (C2M_FLAG_BWD_ATOMIC | C2M_FLAG_FORCE_GENERIC | C2M_FLAG_COORD_GRID | C2M_FLAG_TRUE_DIV | C2M_FLAG_NO_FMA |
+                 C2M_FLAG_DETERMINISTIC | C2M_FLAG_STAGE_NHWC))
+    return false;
+  if (d.N <= 0 || d.C <= 0 || d.H <= 0 || d.W <= 0) return false;
+  // the channels-last conditions of gather_supported() that do not involve the tensors' addresses
+  if ((int64_t)d.N * d.H * d.W >= (1ll << 31) - 1 || (d.C & 3)) return false;
+  if ((int64_t)d.H * d.W * d.C >= (1ll << 30) || d.H >= 32768 || d.W >= 32768 || d.N > 65535) return false;
+  if ((int64_t)d.N * d.H * d.W * (d.C / 4) >= (1ll << 32)) return false;
+  return true;
+}
+
+size_t plan_bytes(const Dims& d) {
+  return plan_supported(d) ? 256 + carve_local(nullptr, d.N, d.H, d.W, d.x_batch, d.C, false).bytes : 0;
+}
+
+// c2m_warp_blend_fwd_plan: clears the plan's counters and hands the forward kernel the arrays it fills
+int plan_bind(const Dims& d, void* plan, size_t bytes, PlanRefs& refs, cudaStream_t st) {
+  const size_t need = plan_bytes(d);
+  if (need == 0) {
+    set_error("c2m_warp_blend_fwd_plan: this configuration has no plan (c2m_warp_plan_bytes() == 0)");
+    return C2M_ERR_INVALID;
+  }
+  if (!plan || bytes < need) {
+    set_error("plan buffer too small: %zu < %zu", bytes, need);
+    return C2M_ERR_WORKSPACE;
+  }
+  const LocalWs w = carve_local(reinterpret_cast<char*>(plan) + 256, d.N, d.H, d.W, d.x_batch, d.C, false);
+  if (cudaMemsetAsync(w.tcnt, 0, w.clear_bytes, st) != cudaSuccess) return memset_failed();
+  refs.pixrec = w.pixrec;
+  refs.tcnt = w.tcnt;
+  refs.tlist = w.tlist;
+  refs.cand_cap = w.cand_cap;
+  refs.ovf = w.ovf;
+  refs.ovf_count = w.ovf_count;
+  refs.ovf_list = w.ovf_list;
+  return C2M_OK;
+}
+
+int launch_plan(const BwdParams& pin, void* plan, size_t bytes, cudaStream_t st) {
+  BwdParams p = pin;
+  const Dims& d = p.d;
+  const size_t need = plan_bytes(d);
+  if (need == 0) {
+    set_error("c2m_warp_plan: this configuration has no plan (c2m_warp_plan_bytes() == 0)");
+    return C2M_ERR_INVALID;
+  }
+  if (!plan || bytes < need) {
+    set_error("plan buffer too small: %zu < %zu", bytes, need);
+    return C2M_ERR_WORKSPACE;
+  }
+  const LocalWs w = carve_local(reinterpret_cast<char*>(plan) + 256, d.N, d.H, d.W, d.x_batch, d.C, false);
+  p.n0 = 0;
+  p.nframes = d.N;
+  p.key_mul = d.C / 4;
+  bind_local(p, w);
+  p.bcount = nullptr;  // float path: incoherent segments take the overflow list
+  p.cnt = nullptr;
+  if (cudaMemsetAsync(w.tcnt, 0, w.clear_bytes, st) != cudaSuccess) return memset_failed();
+  const int segs = d.H * ((d.W + 31) / 32);
+  segbin_kernel<<<dim3((unsigned)((segs + 7) / 8), (unsigned)d.N), 256, 0, st>>>(p);
+  count_launch();
+  return C2M_OK;
+}
+
 int launch_bwd_gather(const BwdParams& pin, Layout lx, void* workspace, size_t workspace_bytes, cudaStream_t st) {
   BwdParams p = pin;
   const Dims& d = p.d;
@@ -1752,20 +1838,10 @@ int launch_bwd_gather(const BwdParams& pin, Layout lx, void* workspace, size_t w
       set_error("workspace too small: %zu < %zu", workspace_bytes, w.bytes);
       return C2M_ERR_WORKSPACE;
     }
-    p.tcnt = w.tcnt;
-    p.bcount = w.bcount; p.bstart = w.bstart; p.bfill = w.bfill; p.pool = w.pool;
-    p.iseg_count = w.iseg_count; p.iseg_list = w.iseg_list;
-    p.flex_count = w.flex_count; p.flex_list = w.flex_list; p.flex_next = w.flex_next;
-    p.tlist = w.tlist;
-    p.cand_cap = w.cand_cap;
-    p.pixrec = w.pixrec;
-    p.gpart = w.gpart;
-    p.ovf_stride = (int64_t)w.ovf_stride;
-    p.cchunk = d.C / w.slices;  // small pyramid level: every pass of this call uses the same channel slicing
-    p.ovf = w.ovf;
-    p.ovf_count = w.ovf_count;
-    p.ovf_list = w.ovf_list;
-    if (cudaMemsetAsync(w.tcnt, 0, w.clear_bytes, st) != cudaSuccess) return memset_failed();
+    bind_local(p, w);
+    // C2M_FLAG_PLANNED: the forward call has already cleared the counters and run segbin_kernel on this workspace
+    const bool planned = (d.flags & C2M_FLAG_PLANNED) && !det;
+    if (!planned && cudaMemsetAsync(w.tcnt, 0, w.clear_bytes, st) != cudaSuccess) return memset_failed();
     if (det) {
       // fixed-point scale from max|gout| * max|mask| (a bound of every |term|), accumulator rows cleared
       p.maxbits = w.maxbits;
@@ -1790,8 +1866,10 @@ int launch_bwd_gather(const BwdParams& pin, Layout lx, void* workspace, size_t w
     // contribution); the float path keeps overflow_kernel's vector reductions, which are faster than the sort
     if (!det || !flex_enabled()) p.bcount = nullptr;
     const int segs = d.H * ((d.W + 31) / 32);  // per frame; grid.y = frames (N <= 65535 checked by gather_supported)
-    segbin_kernel<<<dim3((unsigned)((segs + 7) / 8), (unsigned)d.N), 256, 0, st>>>(p);
-    count_launch();
+    if (!planned) {
+      segbin_kernel<<<dim3((unsigned)((segs + 7) / 8), (unsigned)d.N), 256, 0, st>>>(p);
+      count_launch();
+    }
     if (p.bcount) {
       // incoherent flows: finish the counting sort of their pixels by destination tile (both kernels leave at once
       // when segbin_kernel met no incoherent segment)

@@ -54,6 +54,49 @@ def _dense(t: torch.Tensor, nhwc: bool) -> torch.Tensor:
     return t.contiguous(memory_format=torch.channels_last) if nhwc else t.contiguous()
 
 
+def _nchw_policy() -> str:
+    """What happens to an NCHW-contiguous `x` (the layout the reference's convolutions produce):
+    "propagate" (default) -- x is converted to channels-last ONCE in the forward (c2m_relayout), that copy is what the
+        backward keeps, and out / grad-input come back channels-last strided (same shapes and values; the memory
+        format then propagates through the caller's convolutions like any channels_last tensor);
+    "strict" (C2M_WARP_NCHW=strict or flags=FLAG_STRICT_LAYOUT) -- results keep x's strides: NCHW forward kernel,
+        backward staged through three channels-last copies in the workspace."""
+    return os.environ.get("C2M_WARP_NCHW", "propagate")
+
+
+_NO_PROMOTE = (_lib.FLAG_FORCE_GENERIC | _lib.FLAG_COORD_GRID | _lib.FLAG_BWD_ATOMIC | _lib.FLAG_NO_STAGE |
+               _lib.FLAG_STRICT_LAYOUT | _lib.FLAG_TRUE_DIV | _lib.FLAG_NO_FMA)
+
+
+def _relayout_ok(x: torch.Tensor) -> bool:
+    C = x.shape[1]
+    return x.numel() > 0 and x.shape[0] <= 65535 and C >= 8 and C % 4 == 0 and 4 * x.numel() <= _STAGE_MAX_BYTES
+
+
+def _promotes(x: torch.Tensor, flags: int) -> bool:
+    return _relayout_ok(x) and not (flags & _NO_PROMOTE) and _nchw_policy() != "strict"
+
+
+def _to_channels_last(x: torch.Tensor) -> torch.Tensor:
+    """NCHW-contiguous -> channels-last copy through the library's own relayout kernel (128-bit both ways)."""
+    B, C, H, W = x.shape
+    y = torch.empty_like(x, memory_format=torch.channels_last)
+    with _on_device(x.device):
+        _lib.relayout(x.data_ptr(), y.data_ptr(), B, C, H, W, True, torch.cuda.current_stream().cuda_stream)
+    return y
+
+
+# Plan: the backward's segment registration depends on the flow and the mask only, so the forward kernel -- whose
+# warps hold exactly that geometry -- does it on the side (c2m_warp_blend_fwd_plan, include/c2m_warp.h) and the backward
+# starts with its gather kernel.  C2M_WARP_PLAN=0 switches it off; levels below C2M_WARP_PLAN_MIN_PIXELS output pixels
+# keep the plain calls.
+_PLAN_MIN_PIXELS = int(os.environ.get("C2M_WARP_PLAN_MIN_PIXELS", "0"))
+
+
+def _plan_enabled() -> bool:
+    return os.environ.get("C2M_WARP_PLAN", "1") not in ("", "0")
+
+
 _RESIZE_MODES = {"half_pixel": _lib.RESIZE_HALF_PIXEL, "corners_rescaled": _lib.RESIZE_CORNERS_RESCALE}
 
 # NCHW tensors are staged through channels-last copies in the backward workspace (three tensor-sized buffers) only
@@ -148,6 +191,9 @@ class WarpBlendFunction(torch.autograd.Function):
         _check_inputs(x, flow, mask, other, resized=rs is not None)
         nhwc = _is_nhwc_dense(x)
         x = _dense(x, nhwc)
+        if not nhwc and _promotes(x, flags):
+            x, nhwc = _to_channels_last(x), True  # the channels-last copy is what the backward keeps
+        flags &= ~_lib.FLAG_STRICT_LAYOUT
         flow = flow.contiguous()
         mask = None if mask is None else mask.contiguous()
         other = None if other is None else _dense(other, nhwc)
@@ -156,12 +202,24 @@ class WarpBlendFunction(torch.autograd.Function):
         B, C = x.shape[0], x.shape[1]
         out = torch.empty((N, C, H, W), dtype=x.dtype, device=x.device,
                           memory_format=torch.channels_last if nhwc else torch.contiguous_format)
+        plan = None
         with _on_device(x.device):
             stream = torch.cuda.current_stream().cuda_stream
-            _lib.warp_blend_fwd(_ptr(x), _ptr(flow), _ptr(mask), _ptr(other), _ptr(out), N, C, H, W, B,
-                                x.stride(), out.stride(), padding, flags, stream, rs)
+            if (nhwc and rs is None and not deterministic and ctx.needs_input_grad[0] and _plan_enabled()
+                    and N * H * W >= _PLAN_MIN_PIXELS):
+                nbytes = _lib.plan_bytes(N, C, H, W, B, flags)
+                if nbytes:
+                    plan = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+            if plan is not None:
+                # the forward kernel also registers its row segments for the backward (include/c2m_warp.h)
+                _lib.warp_blend_fwd_plan(_ptr(x), _ptr(flow), _ptr(mask), _ptr(other), _ptr(out), N, C, H, W, B,
+                                         x.stride(), out.stride(), padding, flags, _ptr(plan), nbytes, stream)
+            else:
+                _lib.warp_blend_fwd(_ptr(x), _ptr(flow), _ptr(mask), _ptr(other), _ptr(out), N, C, H, W, B,
+                                    x.stride(), out.stride(), padding, flags, stream, rs)
         ctx.save_for_backward(x, flow, mask, other)  # inputs only: geometry is recomputed in backward
         ctx.cfg = (padding, bool(deterministic), flags, nhwc, rs)
+        ctx.plan = plan
         return out
 
     @staticmethod
@@ -173,7 +231,12 @@ class WarpBlendFunction(torch.autograd.Function):
         need_x, need_flow, need_mask, need_other = ctx.needs_input_grad[:4]
         need_mask = need_mask and mask is not None
         need_other = need_other and other is not None
-        gout = _dense(gout, nhwc)
+        if nhwc and gout.is_contiguous() and not _is_nhwc_dense(gout) and _relayout_ok(gout):
+            # an NCHW upstream gradient for a channels-last result: the library's relayout kernel (copy speed; torch's
+            # strided copy takes three times as long)
+            gout = _to_channels_last(gout)
+        else:
+            gout = _dense(gout, nhwc)
         N = flow.shape[0] * (flow.shape[2] if flow.dim() == 5 else 1)
         H, W = x.shape[2:]
         B, C = x.shape[0], x.shape[1]
@@ -189,10 +252,16 @@ class WarpBlendFunction(torch.autograd.Function):
             # the channels-last kernels (about twice as fast as gathering 4-byte elements at NCHW strides);
             # C2M_WARP_STAGE_MAX_BYTES bounds the extra footprint
             flags |= _lib.FLAG_STAGE_NHWC
+        plan, ctx.plan = ctx.plan, None  # a plan serves one backward (a second one over a retained graph bins again)
         with _on_device(x.device):
             stream = torch.cuda.current_stream().cuda_stream
-            ws_bytes = _lib.bwd_workspace_bytes(N, C, H, W, B, need_x, flags, rs)
-            ws = _workspace(ws_bytes, x.device, stream)
+            if (plan is not None and need_x and not (flags & _lib.FLAG_DETERMINISTIC)
+                    and (gout.data_ptr() | gx.data_ptr() | x.data_ptr()) % 16 == 0):
+                flags |= _lib.FLAG_PLANNED
+                ws, ws_bytes = plan, plan.numel()
+            else:
+                ws_bytes = _lib.bwd_workspace_bytes(N, C, H, W, B, need_x, flags, rs)
+                ws = _workspace(ws_bytes, x.device, stream)
             _lib.warp_blend_bwd(_ptr(x), _ptr(flow), _ptr(mask), _ptr(other), _ptr(gout), _ptr(gx), _ptr(gflow),
                                 _ptr(gmask), _ptr(gother), N, C, H, W, B, x.stride(), gout.stride(), padding,
                                 flags, _ptr(ws), ws_bytes, stream, rs)
@@ -202,7 +271,9 @@ class WarpBlendFunction(torch.autograd.Function):
 def warp_blend(x, flow, mask=None, other=None, padding="border", deterministic=None, flags=0, flow_resize=None):
     """Fused ``resample(x, flow) * mask`` of the reference (ops.py:187-193, generator.py:93).
 
-    x      [B,C,H,W] float32 CUDA, NCHW-contiguous or channels-last (output follows x's format);
+    x      [B,C,H,W] float32 CUDA, channels-last or NCHW-contiguous.  The results follow a channels-last x; an NCHW
+           x with C >= 8, C % 4 == 0 is converted once in the forward and out / grad-input come back channels-last
+           strided (same shape and values; C2M_WARP_NCHW=strict or flags=FLAG_STRICT_LAYOUT keeps x's strides);
            B == N, or B divides N and frame n samples image n % B (the T-fold repeat of
            motion_autoencoder.py:117-119 without materialising it).
     flow   [N,2,H,W] displacement in pixels, channel 0 = x.

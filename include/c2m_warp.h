@@ -147,6 +147,36 @@ C2M_API size_t c2m_warp_bwd_workspace_bytes_rs(int64_t N, int C, int H, int W, i
 /* [N,2,H,W] base grid, bit-identical to the reference's CPU float32 construction. */
 C2M_API int c2m_base_grid(float* grid, int64_t N, int H, int W, void* cuda_stream);
 
+/* Plan of the channels-last float backward.  The first stage of c2m_warp_blend_bwd -- registering every row segment
+ * of 32 output pixels with the destination tiles its samples touch -- depends on the flow and the mask only.  A
+ * caller that knows at forward time that grad-input will be asked for can run it then, on a second stream next to
+ * the forward kernel (that stage is bound by integer instructions, the forward by HBM), into a buffer of
+ * c2m_warp_plan_bytes() bytes, and later pass that buffer as the `workspace` of c2m_warp_blend_bwd together with
+ * C2M_FLAG_PLANNED: the backward then starts with its gather kernel.  c2m_warp_plan_bytes() == 0: this
+ * configuration has no plan (deterministic mode, test-hook flags, sizes beyond the gather's 32-bit limits).  A plan is
+ * consumed by the backward that uses it; x, gout and gx of that backward must be channels-last dense and 16-byte
+ * aligned, the flow / mask not resized (C2M_ERR_INVALID otherwise). */
+#define C2M_FLAG_PLANNED 0x20000
+C2M_API size_t c2m_warp_plan_bytes(int64_t N, int C, int H, int W, int64_t x_batch, int flags);
+C2M_API int c2m_warp_plan(const float* flow, const float* mask, int64_t N, int C, int H, int W, int64_t x_batch,
+                          int padding, int flags, void* plan, size_t plan_bytes, void* cuda_stream);
+/* c2m_warp_blend_fwd that also makes the plan.  With channels-last tensors the forward kernel does it itself: each
+ * of its warps owns one row segment of 32 output pixels and has the sampling geometry in registers, so the
+ * registration rides under the kernel's memory latency and the backward's 0.07 ms stage disappears; any other layout
+ * runs c2m_warp_plan's kernel after the forward on the same stream. */
+C2M_API int c2m_warp_blend_fwd_plan(const float* x, const float* flow, const float* mask, const float* other,
+                                    float* out, int64_t N, int C, int H, int W, int64_t x_batch,
+                                    const int64_t x_strides[4], const int64_t out_strides[4], int padding, int flags,
+                                    void* plan, size_t plan_bytes, void* cuda_stream);
+
+/* Layout change of a dense [N,C,H,W] float32 tensor: NCHW-contiguous -> channels-last (to_channels_last != 0) or
+ * back.  The reference's tensors are NCHW (its convolutions produce them so); the channels-last kernels are the
+ * fast ones on B200, so the Python host converts an NCHW `x` ONCE in the forward, keeps that copy for the backward
+ * and returns channels-last strided results (the memory format then propagates through the caller's
+ * convolutions like any channels_last tensor in PyTorch) instead of staging three tensors in every backward. */
+C2M_API int c2m_relayout(const float* src, float* dst, int64_t N, int C, int H, int W, int to_channels_last,
+                         void* cuda_stream);
+
 /* Forward-splat occlusion map, the producer of the warp's mask (reference src/utils/ops.py:263-275
  * `get_occlusion_map`; with C2M_OCC_COORDS | C2M_OCC_NO_CLAMP: ops.py:205-251 `get_corresponding_map`).
  * in [N,2,H,W] contiguous (flow in pixels, or absolute coordinates), out [N,1,H,W].  The sum is accumulated in

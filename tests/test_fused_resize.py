@@ -60,7 +60,9 @@ def test_apply_optical_fused_resize(dev, case, layout):
     x1, f1, m1 = leaves(x, flow, mask)
     n0 = _lib.launch_count()
     out = c2m_b200.apply_optical(None, x1, f1, m1)
-    assert _lib.launch_count() - n0 == 1, "resize + warp + multiply must be ONE forward launch"
+    # (an NCHW x with C >= 8, C % 4 == 0 is first converted to channels-last: one relayout launch more)
+    converted = layout == "nchw" and C >= 8 and C % 4 == 0
+    assert _lib.launch_count() - n0 == 1 + converted, "resize + warp + multiply must be ONE forward launch"
     g1 = torch.autograd.grad(out, [x1, f1, m1], gout)
     x2, f2, m2 = leaves(x, flow, mask)
     ref = rt.apply_optical(x2, f2, m2)

@@ -132,6 +132,84 @@ def test_golden_vectors(dev, path):
         assert rel(out, torch.from_numpy(o_np)) <= FWD_TOL
 
 
+def test_nchw_input_is_converted_once_and_results_come_back_channels_last(dev):
+    """An NCHW-contiguous x (what the reference's convolutions produce) is converted to channels-last once in the
+    forward; out and grad-input are channels-last strided with the reference's shapes and values, whatever layout the
+    upstream gradient arrives in.  FLAG_STRICT_LAYOUT / C2M_WARP_NCHW=strict keep x's strides (staged backward)."""
+    x, flow, mask, gout = make_inputs(dev, 3, 64, 40, 72, seed=11)
+    ref = run_ref(x, flow, mask, gout)
+    n0 = _lib.launch_count()
+    ours = run_ours(x, flow, mask, gout)
+    launches = _lib.launch_count() - n0
+    check(ours, ref)
+    assert ours[0].is_contiguous(memory_format=torch.channels_last) and not ours[0].is_contiguous()
+    assert ours[1][0].shape == x.shape and ours[1][0].is_contiguous(memory_format=torch.channels_last)
+    # one relayout + the channels-last forward; the backward runs without staging copies
+    n1 = _lib.launch_count()
+    strict = run_ours(x, flow, mask, gout, flags=_lib.FLAG_STRICT_LAYOUT)
+    assert _lib.launch_count() - n1 >= launches + 2  # three staging copies instead of one
+    check(strict, ref)
+    assert strict[0].is_contiguous() and strict[1][0].is_contiguous()
+    # a channels-last upstream gradient (what a channels_last consumer hands back) gives the same bits
+    cl = run_ours(x, flow, mask, gout.contiguous(memory_format=torch.channels_last))
+    assert torch.equal(cl[0], ours[0])
+    for a, b in zip(cl[1][1:], ours[1][1:]):
+        assert torch.equal(a, b)
+    # image-like tensors (C < 8) stay on the NCHW kernels
+    x3, f3, m3, g3 = make_inputs(dev, 2, 3, 24, 40, seed=12)
+    o3 = run_ours(x3, f3, m3, g3)
+    assert o3[0].is_contiguous()
+    check(o3, run_ref(x3, f3, m3, g3))
+
+
+@pytest.mark.parametrize("shape", [(3, 64, 40, 72), (2, 32, 33, 52), (4, 256, 16, 32), (6, 16, 24, 40, 2)],
+                         ids=["c64", "c32_ragged", "sliced_small_level", "frame_repeat"])
+@pytest.mark.parametrize("oob", [False, True], ids=["smooth", "oob"])
+def test_backward_plan_made_in_the_forward(dev, shape, oob, monkeypatch):
+    """c2m_warp_plan: the segment registration runs in the forward call on a second stream and the backward starts
+    with its gather kernel (C2M_FLAG_PLANNED); same results as the backward that bins for itself."""
+    from c2m_b200 import functional as fn
+    N, C, H, W = shape[:4]
+    B = shape[4] if len(shape) > 4 else None
+    x, flow, mask, gout = make_inputs(dev, N, C, H, W, seed=21, oob=oob, B=B)
+    x = x.contiguous(memory_format=torch.channels_last)
+    monkeypatch.setattr(fn, "_PLAN_MIN_PIXELS", 1 << 40)
+    n0 = _lib.launch_count()
+    plain = run_ours(x, flow, mask, gout)
+    plain_launches = _lib.launch_count() - n0
+    monkeypatch.setattr(fn, "_PLAN_MIN_PIXELS", 0)
+    assert _lib.plan_bytes(N, C, H, W, B or N, 0) > 0
+    n0 = _lib.launch_count()
+    planned = run_ours(x, flow, mask, gout)
+    assert _lib.launch_count() - n0 == plain_launches - 1  # the forward kernel does segbin_kernel's work
+    check(planned, run_ref(x, flow, mask, gout, B=B))
+    assert torch.equal(planned[0], plain[0])
+    assert torch.equal(planned[1][1], plain[1][1]) and torch.equal(planned[1][2], plain[1][2])
+    assert rel(planned[1][0], plain[1][0]) <= 1e-5
+    # a retained graph: the second backward has no plan left and bins for itself
+    xr = x.detach().clone().requires_grad_(True)
+    out = c2m_b200.warp_blend(xr, flow, mask)
+    g1, = torch.autograd.grad(out, [xr], gout, retain_graph=True)
+    g2, = torch.autograd.grad(out, [xr], gout)
+    assert rel(g1, g2) <= 1e-5 and rel(g1, plain[1][0]) <= 1e-5
+    # the stand-alone entry (c2m_warp_plan: segbin_kernel into a caller-owned buffer) feeds the same backward
+    Bx = B or N
+    nbytes = _lib.plan_bytes(N, C, H, W, Bx, 0)
+    buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.warp_plan(flow.data_ptr(), mask.data_ptr(), N, C, H, W, Bx, 0, 0, buf.data_ptr(), nbytes, st)
+    gcl = gout.contiguous(memory_format=torch.channels_last)
+    gx, gf, gm = torch.empty_like(x), torch.empty_like(flow), torch.empty_like(mask)
+    _lib.warp_blend_bwd(x.data_ptr(), flow.data_ptr(), mask.data_ptr(), None, gcl.data_ptr(), gx.data_ptr(),
+                        gf.data_ptr(), gm.data_ptr(), None, N, C, H, W, Bx, x.stride(), gcl.stride(), 0,
+                        _lib.FLAG_PLANNED, buf.data_ptr(), nbytes, st)
+    assert torch.equal(gf, plain[1][1]) and torch.equal(gm, plain[1][2]) and rel(gx, plain[1][0]) <= 1e-5
+    # deterministic mode and resized flows have no plan
+    assert _lib.plan_bytes(N, C, H, W, B or N, _lib.FLAG_DETERMINISTIC) == 0
+    det = [run_ours(x, flow, mask, gout, deterministic=True) for _ in range(2)]
+    assert torch.equal(det[0][1][0], det[1][1][0])
+
+
 SHAPES = [
     (2, 64, 32, 64), (1, 3, 64, 128), (3, 5, 17, 23), (2, 8, 7, 11), (1, 1, 1, 1), (2, 4, 1, 9), (2, 4, 9, 1),
     (5, 64, 16, 32), (2, 256, 8, 16), (1, 512, 4, 8), (2, 32, 24, 52), (1, 16, 26, 104), (1, 6, 33, 77),
@@ -140,13 +218,14 @@ SHAPES = [
 
 
 @pytest.mark.parametrize("shape", SHAPES, ids=[str(s) for s in SHAPES])
-@pytest.mark.parametrize("layout", ["nchw", "nhwc"])
+@pytest.mark.parametrize("layout", ["nchw", "nchw_strict", "nhwc"])
 def test_random_shapes_vs_device_reference(dev, shape, layout):
     N, C, H, W = shape
     x, flow, mask, gout = make_inputs(dev, N, C, H, W, seed=sum(shape))
     if layout == "nhwc":
         x = x.contiguous(memory_format=torch.channels_last)
-    ours = run_ours(x, flow, mask, gout)
+    # "nchw": an NCHW x with C >= 8 is converted once and runs the channels-last kernels; "nchw_strict": the NCHW kernels
+    ours = run_ours(x, flow, mask, gout, flags=_lib.FLAG_STRICT_LAYOUT if layout == "nchw_strict" else 0)
     ref = run_ref(x, flow, mask, gout)
     check(ours, ref)
     if layout == "nhwc" and C > 1 and H * W > 1:
@@ -162,8 +241,9 @@ def test_random_shapes_vs_device_reference(dev, shape, layout):
 
 
 @pytest.mark.parametrize("flags", [0, _lib.FLAG_FORCE_GENERIC, _lib.FLAG_NO_TMA, _lib.FLAG_BWD_ATOMIC,
-                                   _lib.FLAG_NO_STAGE, _lib.FLAG_NO_STAGE | _lib.FLAG_NO_TMA],
-                         ids=["default", "generic", "no_tma", "bwd_atomic", "no_stage", "no_stage_no_tma"])
+                                   _lib.FLAG_NO_STAGE, _lib.FLAG_NO_STAGE | _lib.FLAG_NO_TMA,
+                                   _lib.FLAG_STRICT_LAYOUT],
+                         ids=["default", "generic", "no_tma", "bwd_atomic", "no_stage", "no_stage_no_tma", "strict"])
 @pytest.mark.parametrize("layout", ["nchw", "nhwc"])
 def test_kernel_variants_agree(dev, flags, layout):
     x, flow, mask, gout = make_inputs(dev, 3, 24, 40, 72, seed=5)
@@ -219,7 +299,7 @@ def test_channel_sliced_small_levels(dev, cfg):
 @pytest.mark.parametrize("variant", range(0, 6))
 def test_nchw_tile_variants(dev, variant):
     x, flow, mask, gout = make_inputs(dev, 2, 16, 48, 96, seed=6)
-    ours = run_ours(x, flow, mask, gout, flags=variant << 16)
+    ours = run_ours(x, flow, mask, gout, flags=(variant << 24) | _lib.FLAG_STRICT_LAYOUT)
     check(ours, run_ref(x, flow, mask, gout))
 
 

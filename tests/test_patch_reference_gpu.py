@@ -33,9 +33,16 @@ def stub(monkeypatch):
         sys.modules.pop(n, None)
 
 
-def test_patched_stub_tree_runs_the_cuda_kernels(stub):
+@pytest.mark.parametrize("policy", ["strict", "propagate"])
+def test_patched_stub_tree_runs_the_cuda_kernels(stub, policy, monkeypatch):
+    """policy = what happens to the NCHW feature maps the stub's convolutions produce (c2m_b200/functional.py):
+    "strict" keeps their strides, so everything downstream runs exactly as in the unpatched tree and the 1e-4 bound
+    is on this library alone; "propagate" (the default) returns channels-last results, after which cuDNN picks
+    channels-last algorithms for the generator's later convolutions -- their rounding, not the warp's, then sets the
+    error of the gradients that pass through them (bound 2e-3 there)."""
     import c2m_b200
     from c2m_b200 import _lib
+    monkeypatch.setenv("C2M_WARP_NCHW", policy)
     dev = torch.device("cuda", 0)
     torch.manual_seed(3)
     gen = stub["modules.generator.generator"].OcclusionAwareGenerator(16).to(dev)
@@ -77,6 +84,8 @@ def test_patched_stub_tree_runs_the_cuda_kernels(stub):
     assert launched >= 12, f"only {launched} library launches: the patched tree did not reach the CUDA kernels"
     for k, (a, b) in enumerate(zip(ours, ref)):
         tol = 1e-5 if k in (0,) else 1e-4
+        if policy == "propagate" and k < len(ours) - 8:  # the generator's output and gradients (through its convolutions)
+            tol = 2e-3 if k else 1e-4
         assert rel(a, b) <= tol, f"result {k}: {rel(a, b):.3e}"
     assert torch.equal(ours[-1], ref[-1])  # get_grid: bit-identical
     assert set(our_sm) == set(ref_sm)

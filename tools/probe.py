@@ -55,7 +55,7 @@ x, flow, mask, gout = synth(N, C, H, W, False, 1234, dev)
 fb, bb = fwd_bytes(N, C, H, W), bwd_bytes(N, C, H, W)
 tim = {}
 for v in range(6):
-    ms = timeit(lambda: c2m_b200.warp_blend(x, flow, mask, flags=v << 16))
+    ms = timeit(lambda: c2m_b200.warp_blend(x, flow, mask, flags=v << 24))
     tim[f"fwd_nchw_v{v}"] = (ms, fb / ms / 1e6)
 ms = timeit(lambda: c2m_b200.warp_blend(x, flow, mask, flags=_lib.FLAG_NO_TMA))
 tim["fwd_nchw_no_tma"] = (ms, fb / ms / 1e6)
