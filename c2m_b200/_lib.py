@@ -43,7 +43,6 @@ SYMBOLS = (
     "c2m_relayout",
     "c2m_warp_plan_bytes",
     "c2m_warp_plan",
-    "c2m_warp_blend_fwd_plan",
     "c2m_warp_launch_count",
     "c2m_occlusion_map",
     "c2m_occlusion_map_workspace_bytes",
@@ -131,10 +130,6 @@ def load(build_if_missing: bool = False) -> ctypes.CDLL:
         lib.c2m_warp_plan_bytes.argtypes = [_i64, _int, _int, _int, _i64, _int]
         lib.c2m_warp_plan.restype = _int
         lib.c2m_warp_plan.argtypes = [_ptr, _ptr, _i64, _int, _int, _int, _i64, _int, _int, _ptr, ctypes.c_size_t, _ptr]
-        lib.c2m_warp_blend_fwd_plan.restype = _int
-        lib.c2m_warp_blend_fwd_plan.argtypes = [_ptr, _ptr, _ptr, _ptr, _ptr, _i64, _int, _int, _int, _i64,
-                                                ctypes.POINTER(_i64), ctypes.POINTER(_i64), _int, _int, _ptr,
-                                                ctypes.c_size_t, _ptr]
         lib.c2m_relayout.restype = _int
         lib.c2m_relayout.argtypes = [_ptr, _ptr, _i64, _int, _int, _int, _int, _ptr]
         lib.c2m_warp_profile.restype = _int
@@ -195,14 +190,6 @@ def warp_blend_fwd(x_ptr, flow_ptr, mask_ptr, other_ptr, out_ptr, N, C, H, W, x_
     rc = load().c2m_warp_blend_fwd_rs(x_ptr, flow_ptr, mask_ptr, other_ptr, out_ptr, N, C, H, W, x_batch,
                                       strides4(x_strides), strides4(out_strides), resize, padding, flags, stream)
     _check(rc, "c2m_warp_blend_fwd")
-
-
-def warp_blend_fwd_plan(x_ptr, flow_ptr, mask_ptr, other_ptr, out_ptr, N, C, H, W, x_batch, x_strides, out_strides,
-                        padding, flags, plan_ptr, plan_nbytes, stream) -> None:
-    rc = load().c2m_warp_blend_fwd_plan(x_ptr, flow_ptr, mask_ptr, other_ptr, out_ptr, N, C, H, W, x_batch,
-                                        strides4(x_strides), strides4(out_strides), padding, flags, plan_ptr,
-                                        plan_nbytes, stream)
-    _check(rc, "c2m_warp_blend_fwd_plan")
 
 
 def warp_blend_bwd(x_ptr, flow_ptr, mask_ptr, other_ptr, gout_ptr, gx_ptr, gflow_ptr, gmask_ptr, gother_ptr,

@@ -240,10 +240,10 @@ float c2m_warp_profile_last_ms(void) {
 
 static size_t up256(size_t v) { return (v + 255) & ~(size_t)255; }
 
-static int fwd_entry(const float* x, const float* flow, const float* mask, const float* other, float* out,
-                     int64_t N, int C, int H, int W, int64_t x_batch, const int64_t x_strides[4],
-                     const int64_t out_strides[4], const c2m_resize* rs, int padding, int flags, void* plan,
-                     size_t plan_bytes_, void* cuda_stream) {
+int c2m_warp_blend_fwd_rs(const float* x, const float* flow, const float* mask, const float* other, float* out,
+                          int64_t N, int C, int H, int W, int64_t x_batch, const int64_t x_strides[4],
+                          const int64_t out_strides[4], const c2m_resize* rs, int padding, int flags,
+                          void* cuda_stream) {
   FwdParams p;
   memset(&p, 0, sizeof(p));
   int rc = fill_dims(p.d, N, C, H, W, x_batch, padding, flags);
@@ -263,51 +263,9 @@ static int fwd_entry(const float* x, const float* flow, const float* mask, const
   canonical(p.os, out_strides, lo, C, H, W);
   p.x = x; p.flow = flow; p.mask = mask; p.other = other; p.out = out;
   p.cchunk = C;
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
-  bool plan_after = false;
-  if (plan) {
-    if (p.d.rs.on) {
-      set_error("c2m_warp_blend_fwd_plan: a resized flow / mask has no plan");
-      return C2M_ERR_INVALID;
-    }
-    if (fwd_makes_plan(p, lx, lo)) {  // the forward kernel registers its row segments itself
-      if ((rc = plan_bind(p.d, plan, plan_bytes_, p.plan, st)) != C2M_OK) return rc;
-    } else {
-      plan_after = true;  // another forward kernel runs: the plan is made by segbin_kernel right after it
-    }
-  }
-  rc = launch_fwd(p, lx, lo, st);
+  rc = launch_fwd(p, lx, lo, reinterpret_cast<cudaStream_t>(cuda_stream));
   if (rc) return rc;
-  if (plan_after) {
-    BwdParams b;
-    memset(&b, 0, sizeof(b));
-    b.d = p.d;
-    b.flow = flow;
-    b.mask = mask;
-    b.cchunk = C;
-    if ((rc = launch_plan(b, plan, plan_bytes_, st)) != C2M_OK) return rc;
-  }
   return check_launch("c2m_warp_blend_fwd");
-}
-
-int c2m_warp_blend_fwd_rs(const float* x, const float* flow, const float* mask, const float* other, float* out,
-                          int64_t N, int C, int H, int W, int64_t x_batch, const int64_t x_strides[4],
-                          const int64_t out_strides[4], const c2m_resize* rs, int padding, int flags,
-                          void* cuda_stream) {
-  return fwd_entry(x, flow, mask, other, out, N, C, H, W, x_batch, x_strides, out_strides, rs, padding, flags, nullptr,
-                   0, cuda_stream);
-}
-
-int c2m_warp_blend_fwd_plan(const float* x, const float* flow, const float* mask, const float* other, float* out,
-                            int64_t N, int C, int H, int W, int64_t x_batch, const int64_t x_strides[4],
-                            const int64_t out_strides[4], int padding, int flags, void* plan, size_t plan_bytes_,
-                            void* cuda_stream) {
-  if (!plan) {
-    set_error("c2m_warp_blend_fwd_plan: null plan buffer");
-    return C2M_ERR_INVALID;
-  }
-  return fwd_entry(x, flow, mask, other, out, N, C, H, W, x_batch, x_strides, out_strides, nullptr, padding, flags, plan,
-                   plan_bytes_, cuda_stream);
 }
 
 int c2m_warp_blend_fwd(const float* x, const float* flow, const float* mask, const float* other, float* out,

@@ -55,20 +55,7 @@ struct Dims {
   Resize rs;
 };
 
-// Plan of the channels-last float backward written by the forward kernel itself (c2m_warp_blend_fwd_plan): the
-// arrays segbin_kernel fills -- pixel records, candidate segments per destination tile, the overflow list.
-struct PlanRefs {
-  int4* pixrec;  // nullptr: this forward makes no plan
-  int* tcnt;
-  int2* tlist;
-  int cand_cap;
-  unsigned char* ovf;
-  int* ovf_count;
-  int* ovf_list;
-};
-
 struct FwdParams {
-  PlanRefs plan;
   Dims d;
   const float* x;
   const float* flow;
@@ -287,118 +274,6 @@ __device__ __forceinline__ void make_geo(const Dims& d, float fx, float fy, int 
 }
 
 // ---------------------------------------------------------------------------------------------
-// Segment registration of the channels-last float backward, callable from the forward kernel (whose warps own one
-// row segment of 32 output pixels each, exactly segbin_kernel's unit of work).  Same results as segbin_kernel's
-// float path; split in two so that the returning atomic's latency is spent under the forward's row loop:
-//   plan_issue   pixel record, bounding box of the destinations, one atomic per overlapped destination tile
-//   plan_commit  candidate entries (or, when a tile's candidate array is full / the segment is incoherent, the
-//                overflow flags and list -- rare: the geometry is formed again rather than kept in registers)
-constexpr int kPlanTH = 8, kPlanTW = 32, kPlanMaxCells = 12;
-
-struct PlanSeg {
-  int xs0, xs1, ys0, ys1;  // clamped corner columns / rows
-  unsigned act;            // corners that contribute (in the image, weight * mask != 0)
-  int xmin, xmax, ymin, ymax;
-};
-
-__device__ __forceinline__ void plan_geometry(const Dims& d, float fx, float fy, float m, int i, int j, bool live,
-                                              PlanSeg& s, int4& rec) {
-  s.xmin = INT_MAX; s.xmax = INT_MIN; s.ymin = INT_MAX; s.ymax = INT_MIN;
-  s.act = 0u;
-  s.xs0 = s.xs1 = s.ys0 = s.ys1 = 0;
-  if (live) {
-    Geo g;
-    make_geo<true>(d, fx, fy, i, j, g);
-    s.xs0 = g.x0; s.xs1 = g.x1; s.ys0 = g.y0; s.ys1 = g.y1;
-    // unclamped corner (-1 and W / H mark out-of-image neighbours; zeros-padding outliers sit at -100)
-    const int ux0 = g.oknw | g.oksw ? g.x0 : (g.okne | g.okse ? g.x1 - 1 : -100);
-    const int uy0 = g.oknw | g.okne ? g.y0 : (g.oksw | g.okse ? g.y1 - 1 : -100);
-    rec = make_int4((ux0 & 0xffff) | (uy0 << 16), __float_as_int(g.ax), __float_as_int(g.ay), __float_as_int(m));
-    s.act = (unsigned)(g.oknw && g.wnw * m != 0.f) | ((unsigned)(g.okne && g.wne * m != 0.f) << 1) |
-            ((unsigned)(g.oksw && g.wsw * m != 0.f) << 2) | ((unsigned)(g.okse && g.wse * m != 0.f) << 3);
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-      if (s.act & (1u << k)) {
-        const int xk = (k & 1) ? s.xs1 : s.xs0, yk = (k & 2) ? s.ys1 : s.ys0;
-        s.xmin = min(s.xmin, xk); s.xmax = max(s.xmax, xk);
-        s.ymin = min(s.ymin, yk); s.ymax = max(s.ymax, yk);
-      }
-  }
-  s.xmin = __reduce_min_sync(0xffffffffu, s.xmin);
-  s.xmax = __reduce_max_sync(0xffffffffu, s.xmax);
-  s.ymin = __reduce_min_sync(0xffffffffu, s.ymin);
-  s.ymax = __reduce_max_sync(0xffffffffu, s.ymax);
-}
-
-// status (warp-uniform): 0 nothing lands anywhere, 1 registered (dt / slot pending), 2 incoherent segment
-__device__ __forceinline__ int plan_issue(const Dims& d, const PlanRefs& P, int n, int i, int bx, int lane, float fx,
-                                          float fy, float m, int& dt, int& slot) {
-  const int j = bx * kPlanTW + lane;
-  const bool live = j < d.W;
-  PlanSeg s;
-  int4 rec;
-  plan_geometry(d, fx, fy, m, i, j, live, s, rec);
-  if (live) P.pixrec[(int64_t)n * d.H * d.W + i * d.W + j] = rec;
-  dt = -1;
-  slot = 0;
-  if (s.xmax < s.xmin) return 0;
-  const int tiles_x = (d.W + kPlanTW - 1) / kPlanTW, tiles_y = (d.H + kPlanTH - 1) / kPlanTH;
-  const int tx0 = s.xmin / kPlanTW, ty0 = s.ymin / kPlanTH;
-  const int ncols = s.xmax / kPlanTW - tx0 + 1, nrows = s.ymax / kPlanTH - ty0 + 1;
-  const int ncell = ncols * nrows;
-  if (ncell > kPlanMaxCells) return 2;
-  if (lane < ncell) {
-    // lane / ncols without an integer division (lane < 32, ncols <= 12: (lane + 0.5) / ncols is never near an integer)
-    const int cr = __float2int_rd(((float)lane + 0.5f) * __frcp_rn((float)ncols));
-    dt = ((n % d.x_batch) * tiles_y + ty0 + cr) * tiles_x + tx0 + (lane - cr * ncols);
-    slot = atomicAdd(P.tcnt + dt, 1);
-  }
-  return 1;
-}
-
-__device__ __forceinline__ void plan_commit(const Dims& d, const PlanRefs& P, int n, int i, int bx, int lane, float fx,
-                                            float fy, float m, int status, int dt, int slot) {
-  if (status == 0) return;
-  const int HW = d.H * d.W;
-  unsigned fail = 0xffffffffu;
-  if (status == 1) {
-    bool ok = true;
-    if (dt >= 0) {
-      if (slot < P.cand_cap)
-        P.tlist[(int64_t)dt * P.cand_cap + slot] =
-            make_int2(n * HW + i * d.W + bx * kPlanTW, min(kPlanTW, d.W - bx * kPlanTW));
-      else ok = false;
-    }
-    fail = __ballot_sync(0xffffffffu, !ok);
-    if (fail == 0u) return;
-  }
-  const int j = bx * kPlanTW + lane;
-  PlanSeg s;
-  int4 rec;
-  plan_geometry(d, fx, fy, m, i, j, j < d.W, s, rec);
-  const int tx0 = s.xmin / kPlanTW, ty0 = s.ymin / kPlanTH;
-  const int ncols = s.xmax / kPlanTW - tx0 + 1;
-  unsigned ovf = 0;
-#pragma unroll
-  for (int k = 0; k < 4; ++k)
-    if (s.act & (1u << k)) {
-      const int xk = (k & 1) ? s.xs1 : s.xs0, yk = (k & 2) ? s.ys1 : s.ys0;
-      const int cell = (yk / kPlanTH - ty0) * ncols + (xk / kPlanTW - tx0);
-      if (fail == 0xffffffffu || ((fail >> cell) & 1u)) ovf |= 1u << k;
-    }
-  const unsigned has = __ballot_sync(0xffffffffu, ovf != 0u);
-  if (has == 0u) return;
-  int base = 0;
-  if (lane == __ffs(has) - 1) base = atomicAdd(P.ovf_count, __popc(has));
-  base = __shfl_sync(0xffffffffu, base, __ffs(has) - 1);
-  if (ovf) {
-    const int idx = n * HW + i * d.W + j;
-    P.ovf[idx] = (unsigned char)ovf;
-    P.ovf_list[base + __popc(has & ((1u << lane) - 1u))] = idx;
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
 // Deterministic grad-input: every term w * gout is converted to 64-bit fixed point with a power-of-two
 // scale and summed as an integer -- the result does not depend on the order (or on which mechanism adds
 // which term) and is converted back to float once.  scale = 2^(60 - count_log2 - exponent(max |term|)).
@@ -588,7 +463,6 @@ struct TileMaps {
 TileMaps make_tile_maps(const Dims& d, const float* flow, const float* mask, int TH, int TW);
 
 int launch_fwd(const FwdParams& p, Layout lx, Layout lo, cudaStream_t st);
-bool fwd_makes_plan(const FwdParams& p, Layout lx, Layout lo);
 // fused-resize backward helpers (warp_resize.cu): materialise the resized flow / mask; back-propagate their gradients
 int fill_resize(Dims& d, const c2m_resize* rs);
 void launch_resize_fwd(const Dims& d, const float* flow_src, const float* mask_src, float* flow_out, float* mask_out,
@@ -598,7 +472,6 @@ void launch_resize_bwd(const Dims& d, const float* gflow_small, const float* gma
 int launch_bwd(const BwdParams& p, Layout lx, Layout lg, void* workspace, size_t workspace_bytes, cudaStream_t st);
 void launch_relayout(const float* in, float* out, int64_t n, int C, int HW, bool to_nhwc, cudaStream_t st);
 size_t plan_bytes(const Dims& d);
-int plan_bind(const Dims& d, void* plan, size_t bytes, PlanRefs& refs, cudaStream_t st);
 int launch_plan(const BwdParams& p, void* plan, size_t bytes, cudaStream_t st);
 size_t bwd_workspace_bytes(int64_t N, int C, int H, int W, int64_t x_batch, int want_gx, int flags);
 

@@ -145,9 +145,12 @@ __global__ void __launch_bounds__(256) segbin_kernel(const BwdParams p) {
   const int tiles_x = (d.W + TW - 1) / TW, tiles_y = (d.H + TH - 1) / TH;
   const int lane = threadIdx.x & 31;
   const int n = blockIdx.y;                                 // frame
-  const int rs = blockIdx.x * 8 + (threadIdx.x >> 5);       // segment within the frame
+  const int nb = d.x_batch == d.N ? n : n % d.x_batch;      // image of x the frame samples
+  const int rs = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // segment within the frame
   if (rs >= d.H * tiles_x) return;
-  const int i = rs / tiles_x, bx = rs - i * tiles_x;
+  // (the kernel is bound by integer instructions: no integer divisions on the common path)
+  const int i = d.H * tiles_x < (1 << 20) ? __float2int_rd(((float)rs + 0.5f) * __frcp_rn((float)tiles_x)) : rs / tiles_x;
+  const int bx = rs - i * tiles_x;
   const int j = bx * TW + lane;
   const bool live = j < d.W;
   int xmin = INT_MAX, xmax = INT_MIN, ymin = INT_MAX, ymax = INT_MIN;
@@ -167,7 +170,7 @@ __global__ void __launch_bounds__(256) segbin_kernel(const BwdParams p) {
   // out-of-bounds flows and adds 70 % for coherent ones)
   auto tally = [&](unsigned ovfbits) {
     if (!p.cnt) return;
-    int* c0 = p.cnt + (n % d.x_batch) * HW;
+    int* c0 = p.cnt + nb * HW;
 #pragma unroll
     for (int k = 0; k < 4; ++k)
       if (inimg & (1u << k)) {
@@ -212,8 +215,8 @@ __global__ void __launch_bounds__(256) segbin_kernel(const BwdParams p) {
     tally(0u);
     return;
   }
-  const int tx0 = xmin / TW, ty0 = ymin / TH;
-  const int ncols = xmax / TW - tx0 + 1, nrows = ymax / TH - ty0 + 1;
+  const int tx0 = xmin >> 5, ty0 = ymin >> 3;  // (TW = 32, TH = 8; clamped corners are never negative)
+  const int ncols = (xmax >> 5) - tx0 + 1, nrows = (ymax >> 3) - ty0 + 1;
   const int ncell = ncols * nrows;
   unsigned fail;
   if (ncell > kMaxCells && p.bcount) {
@@ -222,7 +225,7 @@ __global__ void __launch_bounds__(256) segbin_kernel(const BwdParams p) {
     // tiles' grad-input) -- no per-contribution atomics on grad-input, in deterministic mode none on the accumulator
     int tl[4] = {-1, -1, -1, -1};
     if (live) rec_tiles(d, r_ux0, r_uy0, r_ax, r_ay, r_m, tiles_x, tl);
-    int* bc = p.bcount + (n % d.x_batch) * tiles_y * tiles_x;
+    int* bc = p.bcount + nb * tiles_y * tiles_x;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       // clamped out-of-bounds flows send most of a segment to the same border tile: one atomic per distinct tile
@@ -240,13 +243,15 @@ __global__ void __launch_bounds__(256) segbin_kernel(const BwdParams p) {
       // p.incoh_thresh of them zero_hot_rows_kernel clears all its rows, and later segments need not flag
       // their destinations one by one (with fully incoherent flows that is four atomics per pixel saved)
       int k = 0;
-      if (lane == 0) k = atomicAdd(p.incoh + n % d.x_batch, 1);
+      if (lane == 0) k = atomicAdd(p.incoh + nb, 1);
       all_hot = __shfl_sync(0xffffffffu, k, 0) >= p.incoh_thresh;
     }
   } else {
     bool ok = true;
     if (lane < ncell) {
-      const int dt = ((n % d.x_batch) * tiles_y + ty0 + lane / ncols) * tiles_x + tx0 + lane % ncols;
+      // lane / ncols: lane < 32, ncols <= 12 -- (lane + 0.5) / ncols is never near an integer
+      const int cr = __float2int_rd(((float)lane + 0.5f) * __frcp_rn((float)ncols));
+      const int dt = (nb * tiles_y + ty0 + cr) * tiles_x + tx0 + (lane - cr * ncols);
       const int slot = atomicAdd(p.tcnt + dt, 1);
       if (slot < p.cand_cap)
         p.tlist[(int64_t)dt * p.cand_cap + slot] = make_int2(n * HW + i * d.W + bx * TW, min(TW, d.W - bx * TW));
@@ -262,7 +267,7 @@ __global__ void __launch_bounds__(256) segbin_kernel(const BwdParams p) {
 #pragma unroll
   for (int k = 0; k < 4; ++k)
     if (act[k]) {
-      const int cell = (ys[k] / TH - ty0) * ncols + (xs[k] / TW - tx0);
+      const int cell = ((ys[k] >> 3) - ty0) * ncols + ((xs[k] >> 5) - tx0);
       if (fail == 0xffffffffu || ((fail >> cell) & 1u)) ovf |= 1u << k;
     }
   // each pixel belongs to exactly one segment and no gather CTA runs yet: a plain byte store is race free
@@ -1769,29 +1774,6 @@ size_t plan_bytes(const Dims& d) {
   return plan_supported(d) ? 256 + carve_local(nullptr, d.N, d.H, d.W, d.x_batch, d.C, false).bytes : 0;
 }
 
-// c2m_warp_blend_fwd_plan: clears the plan's counters and hands the forward kernel the arrays it fills
-int plan_bind(const Dims& d, void* plan, size_t bytes, PlanRefs& refs, cudaStream_t st) {
-  const size_t need = plan_bytes(d);
-  if (need == 0) {
-    set_error("c2m_warp_blend_fwd_plan: this configuration has no plan (c2m_warp_plan_bytes() == 0)");
-    return C2M_ERR_INVALID;
-  }
-  if (!plan || bytes < need) {
-    set_error("plan buffer too small: %zu < %zu", bytes, need);
-    return C2M_ERR_WORKSPACE;
-  }
-  const LocalWs w = carve_local(reinterpret_cast<char*>(plan) + 256, d.N, d.H, d.W, d.x_batch, d.C, false);
-  if (cudaMemsetAsync(w.tcnt, 0, w.clear_bytes, st) != cudaSuccess) return memset_failed();
-  refs.pixrec = w.pixrec;
-  refs.tcnt = w.tcnt;
-  refs.tlist = w.tlist;
-  refs.cand_cap = w.cand_cap;
-  refs.ovf = w.ovf;
-  refs.ovf_count = w.ovf_count;
-  refs.ovf_list = w.ovf_list;
-  return C2M_OK;
-}
-
 int launch_plan(const BwdParams& pin, void* plan, size_t bytes, cudaStream_t st) {
   BwdParams p = pin;
   const Dims& d = p.d;
@@ -1813,7 +1795,14 @@ int launch_plan(const BwdParams& pin, void* plan, size_t bytes, cudaStream_t st)
   p.cnt = nullptr;
   if (cudaMemsetAsync(w.tcnt, 0, w.clear_bytes, st) != cudaSuccess) return memset_failed();
   const int segs = d.H * ((d.W + 31) / 32);
-  segbin_kernel<<<dim3((unsigned)((segs + 7) / 8), (unsigned)d.N), 256, 0, st>>>(p);
+  // small blocks: next to a running forward kernel (which leaves 4 K registers and 512 threads of an SM free) one
+  // 128-thread block still fits
+  static const int wpb = [] {
+    const char* e = getenv("C2M_WARP_PLAN_THREADS");
+    const int t = e && *e ? atoi(e) : 128;
+    return t >= 32 && t <= 256 ? t / 32 : 4;
+  }();
+  segbin_kernel<<<dim3((unsigned)((segs + wpb - 1) / wpb), (unsigned)d.N), wpb * 32, 0, st>>>(p);
   count_launch();
   return C2M_OK;
 }

@@ -229,8 +229,7 @@ __device__ __forceinline__ void fwd_nhwc_rows(const uint4* __restrict__ off_row,
 // groups: four 128-bit corner loads issued back to back, one 128-bit streaming store.
 //   LP  lanes per pixel (a warp moves 32/LP pixels side by side)
 //   QI  float4 groups per lane when C/4 == LP*QI exactly, 0 = run-time channel loop
-//   PLAN  the warp also registers its row segment for the backward (plan_issue / plan_commit, common.cuh)
-template <int LP, int QI, bool HAS_MASK, bool USE_TMA, bool PLAN = false>
+template <int LP, int QI, bool HAS_MASK, bool USE_TMA>
 __global__ void __launch_bounds__(256, 6) fwd_nhwc_kernel(const __grid_constant__ FwdParams p,
                                                           const __grid_constant__ CUtensorMap tm_flow,
                                                           const __grid_constant__ CUtensorMap tm_mask) {
@@ -296,8 +295,6 @@ __global__ void __launch_bounds__(256, 6) fwd_nhwc_kernel(const __grid_constant_
     const int ok = (int)g.oknw | ((int)g.okne << 1) | ((int)g.oksw << 2) | ((int)g.okse << 3);
     s_mk[warp][lane] = make_float2(m, __int_as_float(ok));
   }
-  int plan_status = 0, plan_dt = -1, plan_slot = 0;
-  if (PLAN && blockIdx.y == 0) plan_status = plan_issue(d, p.plan, n, i, bx, lane, fx, fy, m, plan_dt, plan_slot);
   __syncwarp();
   const int lq = lane % LP, grp = lane / LP;
   const int npx = min(TW, d.W - bx * TW);  // live pixels of this row segment (warp-uniform)
@@ -314,17 +311,6 @@ __global__ void __launch_bounds__(256, 6) fwd_nhwc_kernel(const __grid_constant_
     fwd_nhwc_rows<LP, QI, HAS_MASK, true>(s_off[warp], s_w[warp], s_mk[warp], xl, ol, ot_delta, npx, grp, nq, pxb);
   else
     fwd_nhwc_rows<LP, QI, HAS_MASK, false>(s_off[warp], s_w[warp], s_mk[warp], xl, ol, 0, npx, grp, nq, pxb);
-  if (PLAN && blockIdx.y == 0) {
-    // the flow / mask values again (not kept in registers across the row loop)
-    if (USE_TMA) {
-      fx = s_flow[0][warp][lane];
-      fy = s_flow[1][warp][lane];
-      if (HAS_MASK) m = s_mask[warp][lane];
-    } else if (live) {
-      fetch_flow_mask(d, p.flow, HAS_MASK ? p.mask : nullptr, n, i, j, fx, fy, m);
-    }
-    plan_commit(d, p.plan, n, i, bx, lane, fx, fy, m, plan_status, plan_dt, plan_slot);
-  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -376,13 +362,8 @@ static int launch_nhwc_t(FwdParams p, cudaStream_t st) {
   const Dims& d = p.d;
   const int tiles = d.N * ((d.H + TH - 1) / TH) * ((d.W + TW - 1) / TW);
   const TileMaps tm = make_tile_maps(d, p.flow, p.mask, TH, TW);
-#define C2M_LAUNCH(MASK, TMA)                                                                                       \
-  do {                                                                                                               \
-    if (p.plan.pixrec)                                                                                               \
-      fwd_nhwc_kernel<LP, QI, MASK, TMA, true><<<dim3(tiles, d.C / p.cchunk), TH * TW, 0, st>>>(p, tm.flow, tm.mask); \
-    else                                                                                                             \
-      fwd_nhwc_kernel<LP, QI, MASK, TMA><<<dim3(tiles, d.C / p.cchunk), TH * TW, 0, st>>>(p, tm.flow, tm.mask);      \
-  } while (0)
+#define C2M_LAUNCH(MASK, TMA) \
+  fwd_nhwc_kernel<LP, QI, MASK, TMA><<<dim3(tiles, d.C / p.cchunk), TH * TW, 0, st>>>(p, tm.flow, tm.mask)
   if (p.mask) {
     if (tm.ok) C2M_LAUNCH(true, true); else C2M_LAUNCH(true, false);
   } else {
@@ -419,15 +400,6 @@ static int launch_nhwc(FwdParams p, cudaStream_t st) {
 
 static int launch_fwd_impl(const FwdParams& p, Layout lx, Layout lo, cudaStream_t st);
 
-// does launch_fwd() run the channels-last kernel (the one that can write the backward's plan) for this call?
-bool fwd_makes_plan(const FwdParams& p, Layout lx, Layout lo) {
-  const Dims& d = p.d;
-  const bool generic = (d.flags & (C2M_FLAG_FORCE_GENERIC | C2M_FLAG_COORD_GRID | C2M_FLAG_TRUE_DIV | C2M_FLAG_NO_FMA)) ||
-                       lx != lo || lx == LAYOUT_OTHER || (int64_t)d.H * d.W >= (1ll << 30);
-  return !generic && lx == LAYOUT_NHWC && (d.C % 4) == 0 && ((uintptr_t)p.x % 16) == 0 && ((uintptr_t)p.out % 16) == 0 &&
-         ((uintptr_t)p.other % 16) == 0 && (int64_t)d.H * d.W * d.C < (1ll << 30) && !d.rs.on;
-}
-
 int launch_fwd(const FwdParams& p, Layout lx, Layout lo, cudaStream_t st) {
   profile_begin(st);  // the forward is a single kernel
   const int rc = launch_fwd_impl(p, lx, lo, st);
@@ -450,8 +422,7 @@ static int launch_fwd_impl(const FwdParams& p, Layout lx, Layout lo, cudaStream_
       default: return launch_nchw_t<8, 64, 8>(p, st);
     }
   }
-  // the channels-last kernel addresses corners by 32-bit byte offsets inside one image (it is the only forward
-  // kernel that fills p.plan: fwd_makes_plan() below states the same condition)
+  // the channels-last kernel addresses corners by 32-bit byte offsets inside one image
   if (!generic && lx == LAYOUT_NHWC && (d.C % 4) == 0 && ((uintptr_t)p.x % 16) == 0 && ((uintptr_t)p.out % 16) == 0 &&
       ((uintptr_t)p.other % 16) == 0 &&
       (int64_t)d.H * d.W * d.C < (1ll << 30))

@@ -86,15 +86,23 @@ def _to_channels_last(x: torch.Tensor) -> torch.Tensor:
     return y
 
 
-# Plan: the backward's segment registration depends on the flow and the mask only, so the forward kernel -- whose
-# warps hold exactly that geometry -- does it on the side (c2m_warp_blend_fwd_plan, include/c2m_warp.h) and the backward
-# starts with its gather kernel.  C2M_WARP_PLAN=0 switches it off; levels below C2M_WARP_PLAN_MIN_PIXELS output pixels
-# keep the plain calls.
-_PLAN_MIN_PIXELS = int(os.environ.get("C2M_WARP_PLAN_MIN_PIXELS", "0"))
+# Plan: the backward's segment registration depends on the flow and the mask only, so the forward call runs it on a
+# second stream next to its own (HBM-bound) kernel and the backward starts with its gather kernel (include/c2m_warp.h,
+# c2m_warp_plan).  C2M_WARP_PLAN=0 switches it off; levels below C2M_WARP_PLAN_MIN_PIXELS output pixels are host-bound
+# and keep the one-stream path.
+_PLAN_MIN_PIXELS = int(os.environ.get("C2M_WARP_PLAN_MIN_PIXELS", str(1 << 20)))
+_side_streams = {}
 
 
 def _plan_enabled() -> bool:
     return os.environ.get("C2M_WARP_PLAN", "1") not in ("", "0")
+
+
+def _side_stream(device: torch.device) -> "torch.cuda.Stream":
+    s = _side_streams.get(device.index)
+    if s is None:
+        s = _side_streams[device.index] = torch.cuda.Stream(device=device)
+    return s
 
 
 _RESIZE_MODES = {"half_pixel": _lib.RESIZE_HALF_PIXEL, "corners_rescaled": _lib.RESIZE_CORNERS_RESCALE}
@@ -204,19 +212,23 @@ class WarpBlendFunction(torch.autograd.Function):
                           memory_format=torch.channels_last if nhwc else torch.contiguous_format)
         plan = None
         with _on_device(x.device):
-            stream = torch.cuda.current_stream().cuda_stream
+            cur = torch.cuda.current_stream()
+            stream = cur.cuda_stream
             if (nhwc and rs is None and not deterministic and ctx.needs_input_grad[0] and _plan_enabled()
                     and N * H * W >= _PLAN_MIN_PIXELS):
                 nbytes = _lib.plan_bytes(N, C, H, W, B, flags)
                 if nbytes:
                     plan = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+                    side = _side_stream(x.device)
+                    side.wait_stream(cur)  # the flow / mask (and the buffer's previous life) belong to `cur`
+            _lib.warp_blend_fwd(_ptr(x), _ptr(flow), _ptr(mask), _ptr(other), _ptr(out), N, C, H, W, B,
+                                x.stride(), out.stride(), padding, flags, stream, rs)
             if plan is not None:
-                # the forward kernel also registers its row segments for the backward (include/c2m_warp.h)
-                _lib.warp_blend_fwd_plan(_ptr(x), _ptr(flow), _ptr(mask), _ptr(other), _ptr(out), N, C, H, W, B,
-                                         x.stride(), out.stride(), padding, flags, _ptr(plan), nbytes, stream)
-            else:
-                _lib.warp_blend_fwd(_ptr(x), _ptr(flow), _ptr(mask), _ptr(other), _ptr(out), N, C, H, W, B,
-                                    x.stride(), out.stride(), padding, flags, stream, rs)
+                # launched after the forward kernel, which keeps the scheduler's priority: the plan's small blocks
+                # take the registers and thread slots that kernel leaves free on every SM
+                _lib.warp_plan(_ptr(flow), _ptr(mask), N, C, H, W, B, padding, flags, _ptr(plan), nbytes,
+                               side.cuda_stream)
+                cur.wait_stream(side)  # everything later on `cur` -- the backward, the buffer's release -- is ordered
         ctx.save_for_backward(x, flow, mask, other)  # inputs only: geometry is recomputed in backward
         ctx.cfg = (padding, bool(deterministic), flags, nhwc, rs)
         ctx.plan = plan

@@ -160,15 +160,6 @@ C2M_API int c2m_base_grid(float* grid, int64_t N, int H, int W, void* cuda_strea
 C2M_API size_t c2m_warp_plan_bytes(int64_t N, int C, int H, int W, int64_t x_batch, int flags);
 C2M_API int c2m_warp_plan(const float* flow, const float* mask, int64_t N, int C, int H, int W, int64_t x_batch,
                           int padding, int flags, void* plan, size_t plan_bytes, void* cuda_stream);
-/* c2m_warp_blend_fwd that also makes the plan.  With channels-last tensors the forward kernel does it itself: each
- * of its warps owns one row segment of 32 output pixels and has the sampling geometry in registers, so the
- * registration rides under the kernel's memory latency and the backward's 0.07 ms stage disappears; any other layout
- * runs c2m_warp_plan's kernel after the forward on the same stream. */
-C2M_API int c2m_warp_blend_fwd_plan(const float* x, const float* flow, const float* mask, const float* other,
-                                    float* out, int64_t N, int C, int H, int W, int64_t x_batch,
-                                    const int64_t x_strides[4], const int64_t out_strides[4], int padding, int flags,
-                                    void* plan, size_t plan_bytes, void* cuda_stream);
-
 /* Layout change of a dense [N,C,H,W] float32 tensor: NCHW-contiguous -> channels-last (to_channels_last != 0) or
  * back.  The reference's tensors are NCHW (its convolutions produce them so); the channels-last kernels are the
  * fast ones on B200, so the Python host converts an NCHW `x` ONCE in the forward, keeps that copy for the backward
