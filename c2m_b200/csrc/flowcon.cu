@@ -40,11 +40,18 @@ struct FcPixel {
 
 __device__ __forceinline__ FcPixel fc_decode(const FcParams& p, int64_t idx, int HW) {
   FcPixel q;
-  const int64_t f = idx / HW;
-  q.r = (int)(idx - f * HW);
-  q.b = (int)(f / p.T);
-  q.t = (int)(f - (int64_t)q.b * p.T);
-  q.i = q.r / p.d.W;
+  if (p.total <= 0x7fffffff) {  // 32-bit divisions: the 64-bit ones are emulated (~100 instructions each)
+    const unsigned u = (unsigned)idx, f = u / (unsigned)HW;
+    q.r = (int)(u - f * (unsigned)HW);
+    q.b = (int)(f / (unsigned)p.T);
+    q.t = (int)(f - (unsigned)q.b * (unsigned)p.T);
+  } else {
+    const int64_t f = idx / HW;
+    q.r = (int)(idx - f * HW);
+    q.b = (int)(f / p.T);
+    q.t = (int)(f - (int64_t)q.b * p.T);
+  }
+  q.i = (int)((unsigned)q.r / (unsigned)p.d.W);
   q.j = q.r - q.i * p.d.W;
   q.o2 = (((int64_t)q.b * 2) * p.T + q.t) * HW + q.r;
   q.o1 = ((int64_t)q.b * p.T + q.t) * HW + q.r;
@@ -62,10 +69,14 @@ __device__ __forceinline__ void fc_sample(const float* img, const FcPixel& q, in
   const float* p0 = img + (((int64_t)q.b * 2) * T + q.t) * HW;
   const float* p1 = p0 + (int64_t)T * HW;
   const int onw = g.y0 * W + g.x0, one = g.y0 * W + g.x1, osw = g.y1 * W + g.x0, ose = g.y1 * W + g.x1;
-  tp.v[0][0] = g.oknw ? __ldg(p0 + onw) : 0.f; tp.v[0][1] = g.okne ? __ldg(p0 + one) : 0.f;
-  tp.v[0][2] = g.oksw ? __ldg(p0 + osw) : 0.f; tp.v[0][3] = g.okse ? __ldg(p0 + ose) : 0.f;
-  tp.v[1][0] = g.oknw ? __ldg(p1 + onw) : 0.f; tp.v[1][1] = g.okne ? __ldg(p1 + one) : 0.f;
-  tp.v[1][2] = g.oksw ? __ldg(p1 + osw) : 0.f; tp.v[1][3] = g.okse ? __ldg(p1 + ose) : 0.f;
+  // eight loads requested back to back (the corners are clamped into the image: every load is legal), then the
+  // out-of-image ones zeroed
+  tp.v[0][0] = __ldg(p0 + onw); tp.v[0][1] = __ldg(p0 + one); tp.v[0][2] = __ldg(p0 + osw); tp.v[0][3] = __ldg(p0 + ose);
+  tp.v[1][0] = __ldg(p1 + onw); tp.v[1][1] = __ldg(p1 + one); tp.v[1][2] = __ldg(p1 + osw); tp.v[1][3] = __ldg(p1 + ose);
+  if (!g.oknw) tp.v[0][0] = tp.v[1][0] = 0.f;
+  if (!g.okne) tp.v[0][1] = tp.v[1][1] = 0.f;
+  if (!g.oksw) tp.v[0][2] = tp.v[1][2] = 0.f;
+  if (!g.okse) tp.v[0][3] = tp.v[1][3] = 0.f;
   w0 = fmaf(tp.v[0][3], g.wse, fmaf(tp.v[0][2], g.wsw, fmaf(tp.v[0][1], g.wne, tp.v[0][0] * g.wnw)));
   w1 = fmaf(tp.v[1][3], g.wse, fmaf(tp.v[1][2], g.wsw, fmaf(tp.v[1][1], g.wne, tp.v[1][0] * g.wnw)));
 }

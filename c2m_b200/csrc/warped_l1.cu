@@ -62,6 +62,30 @@ __device__ __forceinline__ float l1_sample(const float* xc, const Geo& g, int W,
   return fmaf(vse, g.wse, fmaf(vsw, g.wsw, fmaf(vne, g.wne, vnw * g.wnw)));
 }
 
+// The four corner values of CT channel planes, requested back to back before the first use (the corners are clamped
+// into the image, so every load is legal; out-of-image ones are zeroed afterwards): one exposed memory round trip per
+// pixel instead of one per channel.
+template <int CT>
+__device__ __forceinline__ void l1_gather(const float* xc, const Geo& g, int W, int HW, float (&v)[CT][4]) {
+  const int onw = g.y0 * W + g.x0, one = g.y0 * W + g.x1, osw = g.y1 * W + g.x0, ose = g.y1 * W + g.x1;
+#pragma unroll
+  for (int c = 0; c < CT; ++c) {
+    v[c][0] = __ldg(xc + c * HW + onw);
+    v[c][1] = __ldg(xc + c * HW + one);
+    v[c][2] = __ldg(xc + c * HW + osw);
+    v[c][3] = __ldg(xc + c * HW + ose);
+  }
+#pragma unroll
+  for (int c = 0; c < CT; ++c) {
+    if (!g.oknw) v[c][0] = 0.f;
+    if (!g.okne) v[c][1] = 0.f;
+    if (!g.oksw) v[c][2] = 0.f;
+    if (!g.okse) v[c][3] = 0.f;
+  }
+}
+
+// CT: compile-time channel count (3: the frames of losses.py:219-222), 0 = run-time channel loop
+template <int CT>
 __global__ void __launch_bounds__(256, 4) warped_l1_fwd_kernel(const L1Params p, double* __restrict__ partials) {
   __shared__ float s_warp[8];
   const Dims& d = p.d;
@@ -81,12 +105,22 @@ __global__ void __launch_bounds__(256, 4) warped_l1_fwd_kernel(const L1Params p,
     make_geo<false>(d, fx, fy, q.i, q.j, g);
     const float* xc = p.src + (int64_t)q.b * d.C * HW;
     const float* tc = p.tgt + ((int64_t)q.b * d.C * p.T + q.t) * HW + q.r;
-    for (int c = 0; c < d.C; ++c) {
-      float a, b2, c2, e;
-      const float w = l1_sample(xc, g, d.W, a, b2, c2, e);
-      acc += fabsf(w - __ldg(tc));
-      xc += HW;
-      tc += (int64_t)p.T * HW;
+    if (CT > 0) {
+      float v[CT > 0 ? CT : 1][4], tg[CT > 0 ? CT : 1];
+      l1_gather<(CT > 0 ? CT : 1)>(xc, g, d.W, HW, v);
+#pragma unroll
+      for (int c = 0; c < CT; ++c) tg[c] = __ldg(tc + (int64_t)c * p.T * HW);
+#pragma unroll
+      for (int c = 0; c < CT; ++c)
+        acc += fabsf(fmaf(v[c][3], g.wse, fmaf(v[c][2], g.wsw, fmaf(v[c][1], g.wne, v[c][0] * g.wnw))) - tg[c]);
+    } else {
+      for (int c = 0; c < d.C; ++c) {
+        float a, b2, c2, e;
+        const float w = l1_sample(xc, g, d.W, a, b2, c2, e);
+        acc += fabsf(w - __ldg(tc));
+        xc += HW;
+        tc += (int64_t)p.T * HW;
+      }
     }
   }
 #pragma unroll
@@ -118,6 +152,7 @@ __global__ void __launch_bounds__(256) warped_l1_finish_kernel(const double* __r
 
 // d loss / d flows (and, optionally, d loss / d targets): g = gloss / numel, s_c = sign(warped_c - target_c)
 //   gflow_x = g * sum_c s_c * d warped_c / d ix * d ix / d flow_x     (the coordinate algebra of make_geo<true>)
+template <int CT>
 __global__ void __launch_bounds__(256, 3) warped_l1_bwd_kernel(const L1Params p, const float* __restrict__ gloss,
                                                             double numel, float* __restrict__ gflows,
                                                             float* __restrict__ gtargets) {
@@ -139,15 +174,29 @@ __global__ void __launch_bounds__(256, 3) warped_l1_bwd_kernel(const L1Params p,
     const float* xc = p.src + (int64_t)q.b * d.C * HW;
     int64_t to = ((int64_t)q.b * d.C * p.T + q.t) * HW + q.r;
     float gix = 0.f, giy = 0.f;
-    for (int c = 0; c < d.C; ++c) {
-      float vnw, vne, vsw, vse;
-      const float diff = l1_sample(xc, g, d.W, vnw, vne, vsw, vse) - __ldg(p.tgt + to);
-      const float sg = diff > 0.f ? gs : (diff < 0.f ? -gs : (diff == 0.f ? 0.f : diff));  // NaN stays NaN
+    // one channel's share of the gradients (sg = sign(warped - target) * gloss / numel; NaN stays NaN)
+    auto term = [&](float vnw, float vne, float vsw, float vse, float tgt, int64_t at) {
+      const float diff = fmaf(vse, g.wse, fmaf(vsw, g.wsw, fmaf(vne, g.wne, vnw * g.wnw))) - tgt;
+      const float sg = diff > 0.f ? gs : (diff < 0.f ? -gs : (diff == 0.f ? 0.f : diff));
       gix = fmaf(sg, (vne - vnw) * (1.f - g.ay) + (vse - vsw) * g.ay, gix);
       giy = fmaf(sg, (vsw - vnw) * (1.f - g.ax) + (vse - vne) * g.ax, giy);
-      if (gtargets) gtargets[to] = -sg;
-      xc += HW;
-      to += (int64_t)p.T * HW;
+      if (gtargets) gtargets[at] = -sg;
+    };
+    if (CT > 0) {
+      float v[CT > 0 ? CT : 1][4], tg[CT > 0 ? CT : 1];
+      l1_gather<(CT > 0 ? CT : 1)>(xc, g, d.W, HW, v);
+#pragma unroll
+      for (int c = 0; c < CT; ++c) tg[c] = __ldg(p.tgt + to + (int64_t)c * p.T * HW);
+#pragma unroll
+      for (int c = 0; c < CT; ++c) term(v[c][0], v[c][1], v[c][2], v[c][3], tg[c], to + (int64_t)c * p.T * HW);
+    } else {
+      for (int c = 0; c < d.C; ++c) {
+        float vnw, vne, vsw, vse;
+        (void)l1_sample(xc, g, d.W, vnw, vne, vsw, vse);
+        term(vnw, vne, vsw, vse, __ldg(p.tgt + to), to);
+        xc += HW;
+        to += (int64_t)p.T * HW;
+      }
     }
     if (gflows) {
       gflows[fo] = gix * g.gmx;
@@ -211,7 +260,8 @@ int c2m_warped_l1_fwd(const float* source, const float* flows, const float* targ
       return C2M_ERR_INVALID;
     }
     nb = (int)l1_grid(p.total);
-    warped_l1_fwd_kernel<<<nb, 256, 0, st>>>(p, partials);
+    if (C == 3) warped_l1_fwd_kernel<3><<<nb, 256, 0, st>>>(p, partials);
+    else warped_l1_fwd_kernel<0><<<nb, 256, 0, st>>>(p, partials);
     count_launch();
   }
   warped_l1_finish_kernel<<<1, 256, 0, st>>>(partials, nb, numel, loss);
@@ -242,7 +292,10 @@ int c2m_warped_l1_bwd(const float* source, const float* flows, const float* targ
     set_error("null pointer argument");
     return C2M_ERR_INVALID;
   }
-  warped_l1_bwd_kernel<<<l1_grid(p.total), 256, 0, st>>>(p, gloss, (double)p.total * (double)C, gflows, gtargets);
+  if (C == 3)
+    warped_l1_bwd_kernel<3><<<l1_grid(p.total), 256, 0, st>>>(p, gloss, (double)p.total * (double)C, gflows, gtargets);
+  else
+    warped_l1_bwd_kernel<0><<<l1_grid(p.total), 256, 0, st>>>(p, gloss, (double)p.total * (double)C, gflows, gtargets);
   count_launch();
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {

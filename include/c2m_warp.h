@@ -60,7 +60,7 @@ extern "C" {
 #define C2M_API
 #endif
 
-#define C2M_WARP_VERSION 200
+#define C2M_WARP_VERSION 210
 
 /* padding (ATen GridSamplerPadding): the reference path uses border (ops.py:184); zeros is the
  * flavour of src/modules/motion_estimator/dense_motion.py:167 */

@@ -26,7 +26,7 @@ def test_library_loads_and_exports_every_symbol():
     lib = _lib.load()
     for name in _declared_symbols():
         assert getattr(lib, name) is not None
-    assert lib.c2m_warp_version() == 200
+    assert lib.c2m_warp_version() == 210
 
 
 def test_dynamic_symbol_table_has_only_the_abi():
