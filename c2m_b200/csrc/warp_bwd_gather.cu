@@ -138,16 +138,13 @@ __device__ __forceinline__ int rec_tiles(const Dims& d, int ux0, int uy0, float 
   return nt;
 }
 
-__global__ void __launch_bounds__(256) segbin_kernel(const BwdParams p) {
+// one row segment: frame n, segment rs of the frame (row-major over (image row, 32-pixel column block))
+__device__ __forceinline__ void segbin_segment(const BwdParams& p, const int n, const int rs, const int lane) {
   constexpr int TH = 8, TW = 32, kMaxCells = 12;
   const Dims& d = p.d;
   const int HW = d.H * d.W;
   const int tiles_x = (d.W + TW - 1) / TW, tiles_y = (d.H + TH - 1) / TH;
-  const int lane = threadIdx.x & 31;
-  const int n = blockIdx.y;                                 // frame
   const int nb = d.x_batch == d.N ? n : n % d.x_batch;      // image of x the frame samples
-  const int rs = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // segment within the frame
-  if (rs >= d.H * tiles_x) return;
   // (the kernel is bound by integer instructions: no integer divisions on the common path)
   const int i = d.H * tiles_x < (1 << 20) ? __float2int_rd(((float)rs + 0.5f) * __frcp_rn((float)tiles_x)) : rs / tiles_x;
   const int bx = rs - i * tiles_x;
@@ -281,6 +278,12 @@ __global__ void __launch_bounds__(256) segbin_kernel(const BwdParams p) {
     p.ovf[idx] = (unsigned char)ovf;
     p.ovf_list[base + __popc(has & ((1u << lane) - 1u))] = idx;
   }
+}
+
+__global__ void __launch_bounds__(256) segbin_kernel(const BwdParams p) {
+  const int rs = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // segment within the frame
+  if (rs >= p.d.H * ((p.d.W + 31) / 32)) return;
+  segbin_segment(p, blockIdx.y, rs, threadIdx.x & 31);
 }
 
 // Deterministic mode: clear the 64-bit accumulator rows of the destinations that can receive terms -- more
@@ -1801,13 +1804,10 @@ int launch_plan(const BwdParams& pin, void* plan, size_t bytes, cudaStream_t st)
   p.cnt = nullptr;
   if (cudaMemsetAsync(w.tcnt, 0, w.clear_bytes, st) != cudaSuccess) return memset_failed();
   const int segs = d.H * ((d.W + 31) / 32);
-  // small blocks: next to a running forward kernel (which leaves 4 K registers and 512 threads of an SM free) one
-  // 128-thread block still fits
-  static const int wpb = [] {
-    const char* e = getenv("C2M_WARP_PLAN_THREADS");
-    const int t = e && *e ? atoi(e) : 128;
-    return t >= 32 && t <= 256 ? t / 32 : 4;
-  }();
+  // 128-thread blocks: next to a running forward kernel (which leaves 4 K registers and 512 threads of an SM free) one
+  // still fits.  (A persistent grid of 1-4 such blocks per SM launched before the forward kernel was measured too: the
+  // registration then takes 0.65-0.98 ms and becomes the critical path of the forward call.)
+  constexpr int wpb = 4;
   segbin_kernel<<<dim3((unsigned)((segs + wpb - 1) / wpb), (unsigned)d.N), wpb * 32, 0, st>>>(p);
   count_launch();
   return C2M_OK;

@@ -86,16 +86,18 @@ def _to_channels_last(x: torch.Tensor) -> torch.Tensor:
     return y
 
 
-# Plan: the backward's segment registration depends on the flow and the mask only, so the forward call runs it on a
-# second stream next to its own (HBM-bound) kernel and the backward starts with its gather kernel (include/c2m_warp.h,
-# c2m_warp_plan).  C2M_WARP_PLAN=0 switches it off; levels below C2M_WARP_PLAN_MIN_PIXELS output pixels are host-bound
-# and keep the one-stream path.
+# Plan (opt-in, C2M_WARP_PLAN=1): the backward's segment registration depends on the flow and the mask only, so the
+# forward call can run it on a second stream (include/c2m_warp.h, c2m_warp_plan) and the backward starts with its
+# gather kernel.  Next to this library's own forward kernel the overlap is small (the registration's SM time does not
+# vanish: -10 us of a 1.50 ms step) and the plan holds 24 B per output pixel until the backward,
+# hence off by default; a caller that can run c2m_warp_plan under unrelated work gains the whole 0.06 ms.  Levels below
+# C2M_WARP_PLAN_MIN_PIXELS output pixels are host-bound and never planned.
 _PLAN_MIN_PIXELS = int(os.environ.get("C2M_WARP_PLAN_MIN_PIXELS", str(1 << 20)))
 _side_streams = {}
 
 
 def _plan_enabled() -> bool:
-    return os.environ.get("C2M_WARP_PLAN", "1") not in ("", "0")
+    return os.environ.get("C2M_WARP_PLAN", "0") not in ("", "0")
 
 
 def _side_stream(device: torch.device) -> "torch.cuda.Stream":
@@ -199,35 +201,43 @@ class WarpBlendFunction(torch.autograd.Function):
         _check_inputs(x, flow, mask, other, resized=rs is not None)
         nhwc = _is_nhwc_dense(x)
         x = _dense(x, nhwc)
-        if not nhwc and _promotes(x, flags):
-            x, nhwc = _to_channels_last(x), True  # the channels-last copy is what the backward keeps
+        promote = not nhwc and _promotes(x, flags)
         flags &= ~_lib.FLAG_STRICT_LAYOUT
         flow = flow.contiguous()
         mask = None if mask is None else mask.contiguous()
-        other = None if other is None else _dense(other, nhwc)
         N = flow.shape[0] * (flow.shape[2] if flow.dim() == 5 else 1)
         H, W = x.shape[2:]
         B, C = x.shape[0], x.shape[1]
-        out = torch.empty((N, C, H, W), dtype=x.dtype, device=x.device,
-                          memory_format=torch.channels_last if nhwc else torch.contiguous_format)
-        plan = None
+        plan = side = None
         with _on_device(x.device):
             cur = torch.cuda.current_stream()
             stream = cur.cuda_stream
-            if (nhwc and rs is None and not deterministic and ctx.needs_input_grad[0] and _plan_enabled()
+            if ((nhwc or promote) and rs is None and not deterministic and ctx.needs_input_grad[0] and _plan_enabled()
                     and N * H * W >= _PLAN_MIN_PIXELS):
                 nbytes = _lib.plan_bytes(N, C, H, W, B, flags)
                 if nbytes:
                     plan = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
                     side = _side_stream(x.device)
                     side.wait_stream(cur)  # the flow / mask (and the buffer's previous life) belong to `cur`
+            plan_first = promote
+            if promote:
+                # NCHW x: the channels-last copy is what the backward keeps.  The plan (integer-bound) runs next to
+                # the conversion (HBM-bound, few registers) and is done before the forward kernel starts
+                x, nhwc = _to_channels_last(x), True
+            if plan is not None and plan_first:
+                _lib.warp_plan(_ptr(flow), _ptr(mask), N, C, H, W, B, padding, flags, _ptr(plan), nbytes,
+                               side.cuda_stream)
+            other = None if other is None else _dense(other, nhwc)
+            out = torch.empty((N, C, H, W), dtype=x.dtype, device=x.device,
+                              memory_format=torch.channels_last if nhwc else torch.contiguous_format)
             _lib.warp_blend_fwd(_ptr(x), _ptr(flow), _ptr(mask), _ptr(other), _ptr(out), N, C, H, W, B,
                                 x.stride(), out.stride(), padding, flags, stream, rs)
             if plan is not None:
-                # launched after the forward kernel, which keeps the scheduler's priority: the plan's small blocks
-                # take the registers and thread slots that kernel leaves free on every SM
-                _lib.warp_plan(_ptr(flow), _ptr(mask), N, C, H, W, B, padding, flags, _ptr(plan), nbytes,
-                               side.cuda_stream)
+                if not plan_first:
+                    # launched after the forward kernel, which keeps the scheduler's priority: the plan's small blocks
+                    # take the registers and thread slots that kernel leaves free on every SM
+                    _lib.warp_plan(_ptr(flow), _ptr(mask), N, C, H, W, B, padding, flags, _ptr(plan), nbytes,
+                                   side.cuda_stream)
                 cur.wait_stream(side)  # everything later on `cur` -- the backward, the buffer's release -- is ordered
         ctx.save_for_backward(x, flow, mask, other)  # inputs only: geometry is recomputed in backward
         ctx.cfg = (padding, bool(deterministic), flags, nhwc, rs)

@@ -174,10 +174,11 @@ def test_backward_plan_made_in_the_forward(dev, shape, oob, monkeypatch):
     B = shape[4] if len(shape) > 4 else None
     x, flow, mask, gout = make_inputs(dev, N, C, H, W, seed=21, oob=oob, B=B)
     x = x.contiguous(memory_format=torch.channels_last)
-    monkeypatch.setattr(fn, "_PLAN_MIN_PIXELS", 1 << 40)
+    monkeypatch.setenv("C2M_WARP_PLAN", "0")
     n0 = _lib.launch_count()
     plain = run_ours(x, flow, mask, gout)
     plain_launches = _lib.launch_count() - n0
+    monkeypatch.setenv("C2M_WARP_PLAN", "1")
     monkeypatch.setattr(fn, "_PLAN_MIN_PIXELS", 0)
     assert _lib.plan_bytes(N, C, H, W, B or N, 0) > 0
     n0 = _lib.launch_count()
@@ -187,6 +188,11 @@ def test_backward_plan_made_in_the_forward(dev, shape, oob, monkeypatch):
     assert torch.equal(planned[0], plain[0])
     assert torch.equal(planned[1][1], plain[1][1]) and torch.equal(planned[1][2], plain[1][2])
     assert rel(planned[1][0], plain[1][0]) <= 1e-5
+    # an NCHW x: the plan runs next to the conversion
+    if B is None:
+        xn = x.contiguous()
+        pn = run_ours(xn, flow, mask, gout)
+        assert torch.equal(pn[0], plain[0]) and torch.equal(pn[1][1], plain[1][1]) and rel(pn[1][0], plain[1][0]) <= 1e-5
     # a retained graph: the second backward has no plan left and bins for itself
     xr = x.detach().clone().requires_grad_(True)
     out = c2m_b200.warp_blend(xr, flow, mask)
