@@ -170,4 +170,4 @@ int main(void) {
     subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(root, "include"), str(src), "-o", str(exe),
                     "-L", libdir, "-lc2m_warp", "-Wl,-rpath," + libdir], check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
-    assert out == ["200", "1", str(2 * 3 * 5 * 8), "1"]
+    assert out == ["210", "1", str(2 * 3 * 5 * 8), "1"]
