@@ -83,6 +83,7 @@ struct BwdParams {
   // deterministic mode
   long long* acc64;         // fixed-point accumulator, same element order as gx
   const unsigned* maxbits;  // bit pattern of max|gout*mask| (channels-last gather: [0] max|gout|, [1] max|mask|)
+  unsigned* maxacc;         // channels-last deterministic gather: segbin_kernel forms those two maxima on its way
   int count_log2;           // ceil(log2(max contributions per destination))
   unsigned char* touched;   // deterministic channels-last gather: [x_batch*H*W] destination has terms in acc64
   int* incoh;               // deterministic channels-last gather: [x_batch] incoherent segments seen per image

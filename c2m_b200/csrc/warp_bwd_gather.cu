@@ -139,6 +139,8 @@ __device__ __forceinline__ int rec_tiles(const Dims& d, int ux0, int uy0, float 
 }
 
 // one row segment: frame n, segment rs of the frame (row-major over (image row, 32-pixel column block))
+//   MAXACC  deterministic mode: the two maxima of the fixed-point scale are formed on the way (p.maxacc)
+template <bool MAXACC>
 __device__ __forceinline__ void segbin_segment(const BwdParams& p, const int n, const int rs, const int lane) {
   constexpr int TH = 8, TW = 32, kMaxCells = 12;
   const Dims& d = p.d;
@@ -178,10 +180,32 @@ __device__ __forceinline__ void segbin_segment(const BwdParams& p, const int n, 
         }
       }
   };
+  float amask = 0.f;  // |mask| of this pixel (deterministic mode: max|mask| is one factor of the fixed-point scale)
+  if (MAXACC) {
+    // deterministic mode: max|gout| (the other factor) over the segment's own 32 rows rides along -- a streaming read
+    // next to this kernel's integer work instead of a separate 0.2 ms pass over gout.  A non-finite value reports
+    // +inf (fmaxf drops a NaN operand: test the sum, which is NaN as soon as one element is).
+    float mx = 0.f;
+    const int n4 = min(TW, d.W - bx * TW) * (d.C >> 2);
+    const float4* row = reinterpret_cast<const float4*>(p.gout + ((int64_t)n * HW + i * d.W + bx * TW) * d.C);
+#pragma unroll 4
+    for (int k = lane; k < n4; k += 32) {
+      const float4 v = __ldg(row + k);
+      const float m4 = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+      const float chk = v.x + v.y + v.z + v.w;
+      mx = (chk == chk) ? fmaxf(mx, m4) : __int_as_float(0x7f800000);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    // (most warps find the running maximum already at least as large: one load instead of a same-address atomic)
+    if (lane == 0 && mx > 0.f && __float_as_uint(mx) > *reinterpret_cast<volatile unsigned*>(p.maxacc))
+      atomicMax(p.maxacc, __float_as_uint(mx));
+  }
   if (live) {
     const float* fl = p.flow + (int64_t)n * 2 * HW + i * d.W + j;
     const float fx = __ldg(fl), fy = __ldg(fl + HW);
     const float m = p.mask ? __ldg(p.mask + (int64_t)n * HW + i * d.W + j) : 1.f;
+    amask = (m == m) ? fabsf(m) : __int_as_float(0x7f800000);
     Geo g;
     make_geo<true>(d, fx, fy, i, j, g);
     ys[0] = ys[1] = g.y0; ys[2] = ys[3] = g.y1;
@@ -203,6 +227,10 @@ __device__ __forceinline__ void segbin_segment(const BwdParams& p, const int n, 
         xmin = min(xmin, xs[k]); xmax = max(xmax, xs[k]);
         ymin = min(ymin, ys[k]); ymax = max(ymax, ys[k]);
       }
+  }
+  if (MAXACC && p.mask) {
+    const unsigned mb = __reduce_max_sync(0xffffffffu, __float_as_uint(amask));  // (non-negative floats order as integers)
+    if (lane == 0 && mb > *reinterpret_cast<volatile unsigned*>(p.maxacc + 1)) atomicMax(p.maxacc + 1, mb);
   }
   xmin = __reduce_min_sync(0xffffffffu, xmin);
   xmax = __reduce_max_sync(0xffffffffu, xmax);
@@ -280,10 +308,11 @@ __device__ __forceinline__ void segbin_segment(const BwdParams& p, const int n, 
   }
 }
 
+template <bool MAXACC>
 __global__ void __launch_bounds__(256) segbin_kernel(const BwdParams p) {
   const int rs = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // segment within the frame
   if (rs >= p.d.H * ((p.d.W + 31) / 32)) return;
-  segbin_segment(p, blockIdx.y, rs, threadIdx.x & 31);
+  segbin_segment<MAXACC>(p, blockIdx.y, rs, threadIdx.x & 31);
 }
 
 // Deterministic mode: clear the 64-bit accumulator rows of the destinations that can receive terms -- more
@@ -1808,7 +1837,7 @@ int launch_plan(const BwdParams& pin, void* plan, size_t bytes, cudaStream_t st)
   // still fits.  (A persistent grid of 1-4 such blocks per SM launched before the forward kernel was measured too: the
   // registration then takes 0.65-0.98 ms and becomes the critical path of the forward call.)
   constexpr int wpb = 4;
-  segbin_kernel<<<dim3((unsigned)((segs + wpb - 1) / wpb), (unsigned)d.N), wpb * 32, 0, st>>>(p);
+  segbin_kernel<false><<<dim3((unsigned)((segs + wpb - 1) / wpb), (unsigned)d.N), wpb * 32, 0, st>>>(p);
   count_launch();
   return C2M_OK;
 }
@@ -1851,18 +1880,21 @@ int launch_bwd_gather(const BwdParams& pin, Layout lx, void* workspace, size_t w
       while ((1ll << (cl - 2)) < cnt) ++cl;
       p.count_log2 = cl;
       if (cudaMemsetAsync(w.maxbits, 0, w.det_clear_bytes, st) != cudaSuccess) return memset_failed();
-      const int64_t ng = (int64_t)d.N * d.C * d.H * d.W;
-      absmax_flat_kernel<<<sm_count() * 8, 256, 0, st>>>(p.gout, ng, w.maxbits);
-      if (p.mask) absmax_flat_kernel<<<sm_count() * 2, 256, 0, st>>>(p.mask, (int64_t)d.N * d.H * d.W, w.maxbits + 1);
-      else set_bits_kernel<<<1, 1, 0, st>>>(w.maxbits + 1, 0x3f800000u);
-      count_launch(2);
+      // the two maxima are formed by segbin_kernel on its way (it reads the mask anyway and streams gout next to
+      // its integer work); without a mask the second factor is 1
+      p.maxacc = w.maxbits;
+      if (!p.mask) {
+        set_bits_kernel<<<1, 1, 0, st>>>(w.maxbits + 1, 0x3f800000u);
+        count_launch();
+      }
     }
     // the counting sort of incoherent segments serves the deterministic mode (it replaces 64-bit atomics per
     // contribution); the float path keeps overflow_kernel's vector reductions, which are faster than the sort
     if (!det || !flex_enabled()) p.bcount = nullptr;
     const int segs = d.H * ((d.W + 31) / 32);  // per frame; grid.y = frames (N <= 65535 checked by gather_supported)
     if (!planned) {
-      segbin_kernel<<<dim3((unsigned)((segs + 7) / 8), (unsigned)d.N), 256, 0, st>>>(p);
+      if (p.maxacc) segbin_kernel<true><<<dim3((unsigned)((segs + 7) / 8), (unsigned)d.N), 256, 0, st>>>(p);
+      else segbin_kernel<false><<<dim3((unsigned)((segs + 7) / 8), (unsigned)d.N), 256, 0, st>>>(p);
       count_launch();
     }
     if (p.bcount) {

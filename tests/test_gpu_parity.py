@@ -163,6 +163,25 @@ def test_nchw_input_is_converted_once_and_results_come_back_channels_last(dev):
     check(o3, run_ref(x3, f3, m3, g3))
 
 
+@pytest.mark.parametrize("shape", [(3, 64, 8, 16), (2, 12, 5, 7), (1, 3, 9, 4), (5, 130, 3, 33), (0, 8, 4, 4)],
+                         ids=["vector", "ragged", "c3", "c130_odd", "empty"])
+def test_relayout_entry_point_is_a_bit_exact_copy(dev, shape):
+    """c2m_relayout: NCHW-contiguous <-> channels-last, 128-bit path and scalar fallback, both directions."""
+    N, C, H, W = shape
+    x = torch.randn(N, C, H, W, device=dev)
+    y = torch.full((N, C, H, W), float("nan"), device=dev).contiguous(memory_format=torch.channels_last)
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.relayout(x.data_ptr(), y.data_ptr(), N, C, H, W, True, st)
+    assert torch.equal(y, x)
+    if N:
+        assert torch.equal(y.permute(0, 2, 3, 1).contiguous().view(-1), x.permute(0, 2, 3, 1).reshape(-1))
+    z = torch.full((N, C, H, W), float("nan"), device=dev)
+    _lib.relayout(y.data_ptr(), z.data_ptr(), N, C, H, W, False, st)
+    assert torch.equal(z, x) and z.is_contiguous()
+    with pytest.raises(_lib.C2MWarpError):
+        _lib.relayout(x.data_ptr(), y.data_ptr(), 70000, C, H, W, True, st)
+
+
 @pytest.mark.parametrize("shape", [(3, 64, 40, 72), (2, 32, 33, 52), (4, 256, 16, 32), (6, 16, 24, 40, 2)],
                          ids=["c64", "c32_ragged", "sliced_small_level", "frame_repeat"])
 @pytest.mark.parametrize("oob", [False, True], ids=["smooth", "oob"])
