@@ -428,7 +428,7 @@ constexpr int kSplitTiles = 1184;  // fewer tiles than this (8 per SM): slice th
 constexpr int kSplitMax = 8;
 constexpr int kListCap = 8;   // global lists (NCHW path): in-line entries per destination; the tail goes through atomics
 constexpr int kLocalCap = 12; // channels-last local binning: entries per destination in shared memory
-constexpr int kLocalCapDet = 16;  // ... in deterministic mode
+constexpr int kLocalCapDet = 14;  // ... in deterministic mode (14: the CTA then uses exactly 40 960 B, see gather_nhwc_kernel)
 constexpr int kCandPerFrame = 96;  // candidate row segments a destination tile can register per source frame
 constexpr int kCandMax = 256;      // ... and in total (8 warps x 32 lanes preload the ids)
 struct ListEntry {
