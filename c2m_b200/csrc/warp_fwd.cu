@@ -229,8 +229,11 @@ __device__ __forceinline__ void fwd_nhwc_rows(const uint4* __restrict__ off_row,
 // groups: four 128-bit corner loads issued back to back, one 128-bit streaming store.
 //   LP  lanes per pixel (a warp moves 32/LP pixels side by side)
 //   QI  float4 groups per lane when C/4 == LP*QI exactly, 0 = run-time channel loop
+#ifndef C2M_FWD_CTAS
+#define C2M_FWD_CTAS 6  // resident CTAs per SM the register budget is set for (tuning switch, tools/build_variants.py)
+#endif
 template <int LP, int QI, bool HAS_MASK, bool USE_TMA>
-__global__ void __launch_bounds__(256, 6) fwd_nhwc_kernel(const __grid_constant__ FwdParams p,
+__global__ void __launch_bounds__(256, C2M_FWD_CTAS) fwd_nhwc_kernel(const __grid_constant__ FwdParams p,
                                                           const __grid_constant__ CUtensorMap tm_flow,
                                                           const __grid_constant__ CUtensorMap tm_mask) {
   constexpr int TH = 8, TW = 32;

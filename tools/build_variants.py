@@ -19,16 +19,22 @@ jobs = []
 for spec in sys.argv[1:]:
     name, _, defs = spec.partition(":")
     flags = [d for d in defs.split(",") if d]
-    obj = os.path.join(out_dir, name + "_gather.o")
-    cmd = [nvcc, *_build.NVCC_FLAGS, *flags, "-c", os.path.join(_build.CSRC, "warp_bwd_gather.cu"), "-o", obj]
-    jobs.append((name, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-for name, obj, pr in jobs:
-    out, _ = pr.communicate()
-    if pr.returncode:
-        raise SystemExit(f"{name}: nvcc failed\n{out}")
-    objs = [os.path.join(_build.PKG, "build", s.replace(".cu", ".o")) for s in _build.SOURCES if s != "warp_bwd_gather.cu"]
+    procs = []
+    for src in _build.SOURCES:  # every source is rebuilt with the switches (a switch may live in any of them)
+        obj = os.path.join(out_dir, name + "_" + src.replace(".cu", ".o"))
+        cmd = [nvcc, *_build.NVCC_FLAGS, *flags, "-c", os.path.join(_build.CSRC, src), "-o", obj]
+        procs.append((obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    jobs.append((name, procs))
+for name, procs in jobs:
+    objs = []
+    for obj, pr in procs:
+        out, _ = pr.communicate()
+        if pr.returncode:
+            raise SystemExit(f"{name}: nvcc failed\n{out}")
+        objs.append(obj)
     lib = os.path.join(out_dir, name + ".so")
-    subprocess.run([nvcc, "-shared", "-o", lib, obj, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler",
+    subprocess.run([nvcc, "-shared", "-o", lib, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler",
                     "-fPIC"], check=True)
-    os.remove(obj)
+    for obj in objs:
+        os.remove(obj)
     print("built", lib)
