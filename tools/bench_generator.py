@@ -43,10 +43,12 @@ def run(mode, args, rank, local_rank, world, dev):
     flow = torch.randn(N, 2, H, W, device=dev, generator=g) * 4
     occ = torch.rand(N, 1, H, W, device=dev, generator=g)
     target = torch.rand(N, 3, H, W, device=dev, generator=g)
-    saved = (cgen.warp_blend, cgen.resample)
+    cls = cgen.OcclusionAwareGenerator
+    saved = (cls.apply_optical, cls.deform_input)
     if mode == "torch":  # the reference composition on the GPU, as the unpatched trainer would run it
-        cgen.warp_blend = lambda x, f, m=None, *a, **k: rt.warp_blend(x, f, m)
-        cgen.resample = rt.resample
+        cls.apply_optical = lambda self, input_ref=None, optical_flow=None, occlusion_map=None: rt.apply_optical(
+            input_ref, optical_flow, occlusion_map)
+        cls.deform_input = staticmethod(rt.deform_input)
 
     def step():
         opt.zero_grad(set_to_none=True)
@@ -69,7 +71,7 @@ def run(mode, args, rank, local_rank, world, dev):
         torch.cuda.synchronize(dev)
         ms = e0.elapsed_time(e1) / args.steps
     finally:
-        cgen.warp_blend, cgen.resample = saved
+        cls.apply_optical, cls.deform_input = saved
     value, ms_max, _ = cdist.aggregate_throughput(N, ms, dev)
     return {"frames_per_s": value, "ms_per_step": ms_max, "loss": float(loss.detach())}
 
