@@ -35,3 +35,44 @@ for chunk in (40, 20, 8, 4, 2, 1):
     e1.record()
     torch.cuda.synchronize()
     print(f"chunk {chunk:3d} frames: relayout + forward {e0.elapsed_time(e1) / 5:.3f} ms")
+
+
+# Second experiment: the same chunks on TWO streams -- the relayout of chunk k+1 runs next to the forward of chunk k
+# (events order them), so the launch tails of one stream are covered by the other while the channels-last copy of a
+# chunk is read back out of L2.
+s_a, s_b = torch.cuda.Stream(), torch.cuda.Stream()
+
+
+def run2(chunk):
+    cur = torch.cuda.current_stream()
+    s_a.wait_stream(cur)
+    s_b.wait_stream(cur)
+    evs = []
+    for n0 in range(0, N, chunk):
+        n = min(chunk, N - n0)
+        _lib.relayout(x[n0:].data_ptr(), xcl[n0:].data_ptr(), n, C, H, W, True, s_a.cuda_stream)
+        ev = torch.cuda.Event()
+        ev.record(s_a)
+        evs.append(ev)
+    for k, n0 in enumerate(range(0, N, chunk)):
+        n = min(chunk, N - n0)
+        s_b.wait_event(evs[k])
+        _lib.warp_blend_fwd(xcl[n0:].data_ptr(), flow[n0:].data_ptr(), mask[n0:].data_ptr(), None, out[n0:].data_ptr(),
+                            n, C, H, W, n, xcl.stride(), out.stride(), 0, 0, s_b.cuda_stream, None)
+    cur.wait_stream(s_a)
+    cur.wait_stream(s_b)
+
+
+ref = out.clone()
+for chunk in (40, 8, 4, 2, 1):
+    for _ in range(3):
+        run2(chunk)
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        run2(chunk)
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"two streams, chunk {chunk:3d} frames: relayout + forward {e0.elapsed_time(e1) / 5:.3f} ms")
