@@ -19,6 +19,7 @@ PAD_ZEROS = 1
 
 FLAG_DETERMINISTIC = 0x1
 FLAG_COORD_GRID = 0x2
+FLAG_ALIGN_CORNERS = 0x4
 FLAG_TRUE_DIV = 0x100
 FLAG_NO_FMA = 0x200
 FLAG_FORCE_GENERIC = 0x400

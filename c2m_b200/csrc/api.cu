@@ -164,7 +164,8 @@ int fill_dims(Dims& d, int64_t N, int C, int H, int W, int64_t x_batch, int padd
   d.N = (int)N; d.C = C; d.H = H; d.W = W;
   d.x_batch = (int)(x_batch > 0 ? x_batch : 1);
   d.padding = padding;
-  d.flags = flags;
+  // (align_corners=True lives in the stride-generic kernels only)
+  d.flags = (flags & C2M_FLAG_ALIGN_CORNERS) ? (flags | C2M_FLAG_FORCE_GENERIC) : flags;
   // fp32 arithmetic exactly as torch.linspace / the reference's python scalars produce it
   d.stepx = 2.0f / (float)(W - 1);
   d.stepy = 2.0f / (float)(H - 1);

@@ -212,6 +212,8 @@ __device__ __forceinline__ float unnormalized(float f, int k, int n, float step,
   // intrinsics keep nvcc from contracting across the reference's materialised temporaries
   const float nf = (PROBE && (flags & C2M_FLAG_TRUE_DIV)) ? __fdiv_rn(f, b) : __fmul_rn(f, inv_b);
   const float c1 = __fadd_rn(__fadd_rn(g, nf), 1.f);
+  // align_corners=True (ATen grid_sampler_unnormalize): ((coord + 1) / 2) * (size - 1)
+  if (PROBE && (flags & C2M_FLAG_ALIGN_CORNERS)) return __fmul_rn(__fmul_rn(c1, 0.5f), (float)(n - 1));
   const float u = (PROBE && (flags & C2M_FLAG_NO_FMA)) ? __fadd_rn(__fmul_rn(c1, (float)n), -1.f)
                                                        : fmaf(c1, (float)n, -1.f);
   return u * 0.5f;
@@ -225,8 +227,13 @@ __device__ __forceinline__ void make_geo(const Dims& d, float fx, float fy, int 
   float sx = d.inv_bw, sy = d.inv_bh;
   if (PROBE && (d.flags & C2M_FLAG_COORD_GRID)) {
     // (fx, fy) is a normalised sampling location (reference utils.grid_sample, ops.py:183-184)
-    ix = fmaf(__fadd_rn(fx, 1.f), (float)d.W, -1.f) * 0.5f;
-    iy = fmaf(__fadd_rn(fy, 1.f), (float)d.H, -1.f) * 0.5f;
+    if (d.flags & C2M_FLAG_ALIGN_CORNERS) {
+      ix = __fmul_rn(__fmul_rn(__fadd_rn(fx, 1.f), 0.5f), (float)(d.W - 1));
+      iy = __fmul_rn(__fmul_rn(__fadd_rn(fy, 1.f), 0.5f), (float)(d.H - 1));
+    } else {
+      ix = fmaf(__fadd_rn(fx, 1.f), (float)d.W, -1.f) * 0.5f;
+      iy = fmaf(__fadd_rn(fy, 1.f), (float)d.H, -1.f) * 0.5f;
+    }
     sx = 1.f;
     sy = 1.f;
   } else {
@@ -268,8 +275,10 @@ __device__ __forceinline__ void make_geo(const Dims& d, float fx, float fy, int 
   g.y0 = min(max(y0, 0), d.H - 1);
   g.y1 = min(max(y1, 0), d.H - 1);
   // ATen: grad_grid = (size/2 * clip_grad) * gix; autograd of ops.py:190 multiplies by 1/((size-1)/2)
-  g.gmx = cgx * (0.5f * (float)d.W) * sx;
-  g.gmy = cgy * (0.5f * (float)d.H) * sy;
+  // (align_corners=True: (size - 1) / 2, grid_sampler_unnormalize_set_grad)
+  const bool align = PROBE && (d.flags & C2M_FLAG_ALIGN_CORNERS);
+  g.gmx = cgx * (0.5f * (float)(align ? d.W - 1 : d.W)) * sx;
+  g.gmy = cgy * (0.5f * (float)(align ? d.H - 1 : d.H)) * sy;
   g.clipx = cgx == 0.f;
   g.clipy = cgy == 0.f;
 }

@@ -64,7 +64,7 @@ def _nchw_policy() -> str:
     return os.environ.get("C2M_WARP_NCHW", "propagate")
 
 
-_NO_PROMOTE = (_lib.FLAG_FORCE_GENERIC | _lib.FLAG_COORD_GRID | _lib.FLAG_BWD_ATOMIC | _lib.FLAG_NO_STAGE |
+_NO_PROMOTE = (_lib.FLAG_FORCE_GENERIC | _lib.FLAG_COORD_GRID | _lib.FLAG_ALIGN_CORNERS | _lib.FLAG_BWD_ATOMIC | _lib.FLAG_NO_STAGE |
                _lib.FLAG_STRICT_LAYOUT | _lib.FLAG_TRUE_DIV | _lib.FLAG_NO_FMA)
 
 
@@ -290,7 +290,8 @@ class WarpBlendFunction(torch.autograd.Function):
         return gx, gflow, gmask, gother, None, None, None, None
 
 
-def warp_blend(x, flow, mask=None, other=None, padding="border", deterministic=None, flags=0, flow_resize=None):
+def warp_blend(x, flow, mask=None, other=None, padding="border", deterministic=None, flags=0, flow_resize=None,
+               align_corners=False):
     """Fused ``resample(x, flow) * mask`` of the reference (ops.py:187-193, generator.py:93).
 
     x      [B,C,H,W] float32 CUDA, channels-last or NCHW-contiguous.  The results follow a channels-last x; an NCHW
@@ -308,8 +309,12 @@ def warp_blend(x, flow, mask=None, other=None, padding="border", deterministic=N
            flow / mask may also be the reference's 5-D clips [B',2,T,h,w] / [B',1,T,h',w']: frame n = t * B' + b reads
            plane (b, :, t) -- the fold torch.cat(torch.unbind(., 2), 0) of motion_autoencoder.py:120-123 without the
            copies -- and their gradients come back 5-D.
+    align_corners  True samples with F.grid_sample's align_corners=True convention (zero flow is then the identity; no
+           call site of the reference uses it -- stride-generic kernels).
     """
     if deterministic is None:
         deterministic = deterministic_default()
+    if align_corners:
+        flags = int(flags) | _lib.FLAG_ALIGN_CORNERS
     return WarpBlendFunction.apply(x, flow, mask, other, _PADDING[padding], bool(deterministic), int(flags),
                                    flow_resize)

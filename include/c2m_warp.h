@@ -70,6 +70,9 @@ extern "C" {
 /* flags */
 #define C2M_FLAG_DETERMINISTIC 0x1  /* bwd: bitwise run-to-run reproducible grad-input */
 #define C2M_FLAG_COORD_GRID 0x2     /* `flow` is a normalised sampling grid [N,H,W,2] (utils.grid_sample, ops.py:183); gflow has that shape too */
+#define C2M_FLAG_ALIGN_CORNERS 0x4  /* sample with align_corners=True: ix = (c + 1) / 2 * (W - 1).  No call site of the
+                                       reference asks for it (its base grid is built for this convention but sampled
+                                       with the other); served by the stride-generic kernels */
 #define C2M_FLAG_TRUE_DIV 0x100     /* probe only: divide by (size-1)/2 (ATen CPU) instead of * reciprocal (ATen CUDA) */
 #define C2M_FLAG_NO_FMA 0x200       /* probe only: unfused (c+1)*size-1 */
 #define C2M_FLAG_FORCE_GENERIC 0x400 /* run the stride-generic kernels (test hook) */

@@ -345,6 +345,28 @@ def test_out_of_bounds_flow_border_and_zeros(dev):
     check(run_ours(x, flow, mask, gout, padding="zeros"), (ref.detach(), list(gref)))
 
 
+@pytest.mark.parametrize("padding", ["border", "zeros"])
+@pytest.mark.parametrize("layout", ["nchw", "nhwc"])
+def test_align_corners_variant(dev, padding, layout):
+    """align_corners=True (SURVEY.md 8f row 2 names the variant; no call site of the reference uses it): against
+    F.grid_sample(align_corners=True) on the reference's grid construction, forward and gradients; zero flow is then
+    the identity (the reference's base grid is built for this convention)."""
+    N, C, H, W = 3, 16, 24, 52
+    x, flow, mask, gout = make_inputs(dev, N, C, H, W, seed=41, amp=5.0)
+    flow[2] = make_inputs(dev, N, C, H, W, seed=42, oob=True)[1][2]
+    if layout == "nhwc":
+        x = x.contiguous(memory_format=torch.channels_last)
+    xr, fr, mr = (t.detach().clone().requires_grad_(True) for t in (x, flow, mask))
+    grid = rt.base_grid(N, H, W, dev) + torch.cat([fr[:, 0:1] / ((W - 1.0) / 2.0), fr[:, 1:2] / ((H - 1.0) / 2.0)], 1)
+    ref = F.grid_sample(xr, grid.permute(0, 2, 3, 1), mode="bilinear", padding_mode=padding, align_corners=True) * mr
+    gref = torch.autograd.grad(ref, [xr, fr, mr], gout)
+    check(run_ours(x, flow, mask, gout, padding=padding, align_corners=True), (ref.detach(), list(gref)))
+    det = run_ours(x, flow, mask, gout, padding=padding, align_corners=True, deterministic=True)
+    check(det, (ref.detach(), list(gref)))
+    ident = c2m_b200.warp_blend(x, torch.zeros_like(flow), None, padding=padding, align_corners=True)
+    assert rel(ident, x) <= 2e-5  # (the fp32 coordinate carries a few 1e-6 of a pixel)
+
+
 def test_nonfinite_flow_forward(dev):
     x, flow, mask, gout = make_inputs(dev, 1, 4, 16, 32, seed=8)
     flow[0, 0, 3, 5] = float("nan")
