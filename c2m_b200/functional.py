@@ -30,6 +30,18 @@ def _ptr(t):
     return None if t is None else t.data_ptr()
 
 
+try:  # the raw handle of the current stream without building a torch.cuda.Stream object (4 us per call on the host,
+    _raw_stream = torch._C._cuda_getCurrentRawStream  # which the small pyramid levels feel)
+except AttributeError:  # pragma: no cover
+    _raw_stream = None
+
+
+def _current_stream_ptr(device: torch.device) -> int:
+    if _raw_stream is not None:
+        return _raw_stream(device.index if device.index is not None else torch.cuda.current_device())
+    return torch.cuda.current_stream(device).cuda_stream
+
+
 class _on_device:
     """`with torch.cuda.device(dev)` only when `dev` is not already current (the switch costs ~10 us of host time
     per call, which is most of what the small pyramid levels spend)."""
@@ -82,7 +94,7 @@ def _to_channels_last(x: torch.Tensor) -> torch.Tensor:
     B, C, H, W = x.shape
     y = torch.empty_like(x, memory_format=torch.channels_last)
     with _on_device(x.device):
-        _lib.relayout(x.data_ptr(), y.data_ptr(), B, C, H, W, True, torch.cuda.current_stream().cuda_stream)
+        _lib.relayout(x.data_ptr(), y.data_ptr(), B, C, H, W, True, _current_stream_ptr(x.device))
     return y
 
 
@@ -210,13 +222,14 @@ class WarpBlendFunction(torch.autograd.Function):
         B, C = x.shape[0], x.shape[1]
         plan = side = None
         with _on_device(x.device):
-            cur = torch.cuda.current_stream()
-            stream = cur.cuda_stream
+            cur = None
+            stream = _current_stream_ptr(x.device)
             if ((nhwc or promote) and rs is None and not deterministic and ctx.needs_input_grad[0] and _plan_enabled()
                     and N * H * W >= _PLAN_MIN_PIXELS):
                 nbytes = _lib.plan_bytes(N, C, H, W, B, flags)
                 if nbytes:
                     plan = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+                    cur = torch.cuda.current_stream()
                     side = _side_stream(x.device)
                     side.wait_stream(cur)  # the flow / mask (and the buffer's previous life) belong to `cur`
             plan_first = promote
@@ -276,7 +289,7 @@ class WarpBlendFunction(torch.autograd.Function):
             flags |= _lib.FLAG_STAGE_NHWC
         plan, ctx.plan = ctx.plan, None  # a plan serves one backward (a second one over a retained graph bins again)
         with _on_device(x.device):
-            stream = torch.cuda.current_stream().cuda_stream
+            stream = _current_stream_ptr(x.device)
             if (plan is not None and need_x and not (flags & _lib.FLAG_DETERMINISTIC)
                     and (gout.data_ptr() | gx.data_ptr() | x.data_ptr()) % 16 == 0):
                 flags |= _lib.FLAG_PLANNED
