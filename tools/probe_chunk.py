@@ -76,3 +76,28 @@ for chunk in (40, 8, 4, 2, 1):
     e1.record()
     torch.cuda.synchronize()
     print(f"two streams, chunk {chunk:3d} frames: relayout + forward {e0.elapsed_time(e1) / 5:.3f} ms")
+
+
+# Third experiment: the two-stream schedule captured in a CUDA graph (no host time between the launches: the small
+# chunks above are host-bound) -- the cleanest answer to "does reading the channels-last copy out of L2 pay".
+for chunk in (8, 4, 2, 1):
+    g = torch.cuda.CUDAGraph()
+    cap = torch.cuda.Stream()
+    cap.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(cap):
+        run2(chunk)
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g, stream=cap):
+            run2(chunk)
+    torch.cuda.current_stream().wait_stream(cap)
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"two streams in a CUDA graph, chunk {chunk:3d} frames: relayout + forward {e0.elapsed_time(e1) / 5:.3f} ms")
