@@ -51,6 +51,43 @@ def test_deterministic_selection(monkeypatch):
         torch.use_deterministic_algorithms(False)
 
 
+def test_nchw_policy_and_plan_selection(monkeypatch):
+    """Host policies of c2m_b200/functional.py, decided from tensor metadata and the environment only."""
+    from c2m_b200 import _lib
+    monkeypatch.delenv("C2M_WARP_NCHW", raising=False)
+    feat = torch.empty(2, 64, 8, 16, device="meta")
+    assert functional._promotes(feat, 0)                                    # feature maps are converted once
+    assert not functional._promotes(torch.empty(2, 3, 8, 16, device="meta"), 0)    # image-like tensors are not
+    assert not functional._promotes(torch.empty(2, 10, 8, 16, device="meta"), 0)   # nor C % 4 != 0
+    assert not functional._promotes(torch.empty(0, 64, 8, 16, device="meta"), 0)
+    for flag in (_lib.FLAG_STRICT_LAYOUT, _lib.FLAG_NO_STAGE, _lib.FLAG_FORCE_GENERIC, _lib.FLAG_COORD_GRID,
+                 _lib.FLAG_BWD_ATOMIC, _lib.FLAG_ALIGN_CORNERS):
+        assert not functional._promotes(feat, flag)
+    monkeypatch.setenv("C2M_WARP_NCHW", "strict")
+    assert not functional._promotes(feat, 0) and functional._relayout_ok(feat)
+    monkeypatch.setattr(functional, "_STAGE_MAX_BYTES", 1024)
+    assert not functional._relayout_ok(feat)                                # the copy would exceed the budget
+    # the plan is opt-in
+    monkeypatch.delenv("C2M_WARP_PLAN", raising=False)
+    assert functional._plan_enabled() is False
+    monkeypatch.setenv("C2M_WARP_PLAN", "1")
+    assert functional._plan_enabled() is True
+    # c2m_warp_plan_bytes is a pure function of its arguments (no GPU): 24 B per output pixel and a head, or 0
+    n = _lib.plan_bytes(40, 64, 256, 512, 40, 0)
+    assert 22 * 40 * 256 * 512 < n < 30 * 40 * 256 * 512
+    assert _lib.plan_bytes(40, 64, 256, 512, 40, _lib.FLAG_DETERMINISTIC) == 0
+    assert _lib.plan_bytes(40, 64, 256, 512, 40, _lib.FLAG_FORCE_GENERIC) == 0
+    assert _lib.plan_bytes(40, 66, 256, 512, 40, 0) == 0                    # C % 4 != 0: no channels-last gather
+    assert _lib.plan_bytes(40, 64, 256, 512, 7, 0) == 0                     # x_batch must divide N
+    assert _lib.plan_bytes(70000, 64, 8, 32, 70000, 0) == 0                 # beyond the gather's frame limit
+    # argument errors of the relayout entry point are reported before anything is launched
+    with pytest.raises(_lib.C2MWarpError):
+        _lib.relayout(0, 0, 70000, 8, 4, 4, True, None)
+    with pytest.raises(_lib.C2MWarpError):
+        _lib.relayout(None, None, 2, 8, 4, 4, True, None)
+    _lib.relayout(None, None, 0, 8, 4, 4, True, None)                       # empty: nothing to do
+
+
 def test_patch_reference_rebinds_every_bound_name(monkeypatch):
     fake = {}
     for name in ("utils", "utils.ops", "modules", "modules.generator", "modules.generator.generator",
