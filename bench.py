@@ -477,29 +477,39 @@ def run_ours(args):
                 "generator_encoder": [(32, 256, 512), (64, 128, 256), (128, 64, 128), (256, 32, 64)],
                 "motion_decoder": [(64, 64, 128), (128, 32, 64), (256, 16, 32), (512, 8, 16)],
                 "image": [(3, 256, 512)],
+                # the image warps as the reference differentiates them (generator.py:140 kitti, losses.py:219-222): the
+                # frames are data, no mask, only the flow carries a gradient
+                "image_flow_grad_only": [(3, 256, 512)],
             }
             pyramids = {}
             for name, levels in sets.items():
+                flow_only = name == "image_flow_grad_only"
                 ts = []
                 for (c, h, w) in levels:
                     px, pf, pm, pg = synth(N, c, h, w, False, 77 + rank, dev)
                     if nhwc and c % 4 == 0:
                         px = px.contiguous(memory_format=torch.channels_last)
                         pg = pg.contiguous(memory_format=torch.channels_last)
-                    ts.append((px.requires_grad_(True), pf.requires_grad_(True), pm.requires_grad_(True), pg))
+                    if flow_only:
+                        ts.append((px, pf.requires_grad_(True), None, pg))
+                    else:
+                        ts.append((px.requires_grad_(True), pf.requires_grad_(True), pm.requires_grad_(True), pg))
+
+                def wrt(lv):
+                    return [t for t in lv[:3] if t is not None and t.requires_grad]
 
                 def pstep():
-                    for (px, pf, pm, pg) in ts:
-                        o = c2m_b200.warp_blend(px, pf, pm)
-                        torch.autograd.grad(o, [px, pf, pm], pg)
+                    for lv in ts:
+                        o = c2m_b200.warp_blend(lv[0], lv[1], lv[2])
+                        torch.autograd.grad(o, wrt(lv), lv[3])
 
                 pms, _, _ = _time_steps(pstep, 5, 2, barrier)
 
                 # the way a training step runs them: every level's forward, then ONE backward pass over all of them
                 # (one hand-off to the autograd engine instead of one per level)
                 def pstep_one():
-                    outs = [c2m_b200.warp_blend(px, pf, pm) for (px, pf, pm, _) in ts]
-                    torch.autograd.grad(outs, [t for lv in ts for t in lv[:3]], [lv[3] for lv in ts])
+                    outs = [c2m_b200.warp_blend(lv[0], lv[1], lv[2]) for lv in ts]
+                    torch.autograd.grad(outs, [t for lv in ts for t in wrt(lv)], [lv[3] for lv in ts])
 
                 oms, _, _ = _time_steps(pstep_one, 5, 2, barrier)
                 # the same launches captured once in a CUDA graph and replayed (the entry points only enqueue work
@@ -519,6 +529,8 @@ def run_ours(args):
                 except RuntimeError as e:  # capture not possible: keep the eager figure only
                     print(f"bench.py: pyramid graph capture failed: {e}", file=sys.stderr)
                 pbytes = sum(fwd_bytes(N, c, h, w) + bwd_bytes(N, c, h, w) for (c, h, w) in levels)
+                if flow_only:  # fwd: x, out, flow; bwd: gout, x, flow, grad-flow
+                    pbytes = sum(4 * N * h * w * ((2 * c + 2) + (2 * c + 4)) for (c, h, w) in levels)
                 pyramids[name] = {"levels": [list(l) for l in levels], "ms": pms,
                                   "achieved": pbytes / (pms * 1e-3) / 1e9, "frac": pbytes / (pms * 1e-3) / 1e9 / peak,
                                   "one_backward": {"ms": oms, "achieved": pbytes / (oms * 1e-3) / 1e9,

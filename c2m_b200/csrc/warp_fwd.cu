@@ -133,6 +133,26 @@ __global__ void __launch_bounds__(TH* TW, (TH * TW <= 256) ? 768 / (TH * TW) : 2
           oc += HW;
           otc += HW;
         }
+      } else if (nc == 3) {
+        // image-like tensors (C = 3): all twelve corner values requested before the first use, same arithmetic
+        float v[3][4];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          v[c][0] = __ldg(pnw + (int64_t)c * HW);
+          v[c][1] = __ldg(pne + (int64_t)c * HW);
+          v[c][2] = __ldg(psw + (int64_t)c * HW);
+          v[c][3] = __ldg(pse + (int64_t)c * HW);
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float vnw = g.oknw ? v[c][0] : 0.f, vne = g.okne ? v[c][1] : 0.f;
+          const float vsw = g.oksw ? v[c][2] : 0.f, vse = g.okse ? v[c][3] : 0.f;
+          float acc = vnw * g.wnw;
+          acc = fmaf(vne, g.wne, acc);
+          acc = fmaf(vsw, g.wsw, acc);
+          acc = fmaf(vse, g.wse, acc);
+          st_stream(oc + (int64_t)c * HW, HAS_MASK ? __fmul_rn(acc, m) : acc);
+        }
       } else {
 #pragma unroll UNROLL
         for (int c = 0; c < nc; ++c) {
